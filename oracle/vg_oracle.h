@@ -1,0 +1,218 @@
+/*
+ * vg_oracle.h — CPU ORACLE for the voxgraph hot paths.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C restatement of the reference algorithm used as the checker for
+ * the CUDA product path.  Nothing under voxgraph_b200/ may include, link or call it;
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs do.
+ *
+ * PARITY UNPINNED: the reference (ethz-asl/voxgraph @ bd802b5) ships no tests, golden
+ * vectors or fixtures, and its arithmetic dependencies (voxblox, cblox, minkindr,
+ * Ceres, Eigen) are neither vendored nor installed, so neither the reference nor its
+ * dependencies can be compiled here.  The restatement follows the reference sources
+ * line by line where they exist under /root/reference (cited per function below) and
+ * the published upstream algorithms elsewhere; it is pinned
+ * by analytic known-answer tests (tests/test_oracle_*.py) and by golden vectors
+ * generated from the reference's own sympy derivation
+ * (voxgraph/scripts/jacobians_xyz_yaw.py -> tests/golden/).
+ *
+ * Paths are relative to /root/reference/voxgraph/.
+ */
+#ifndef VG_ORACLE_H_
+#define VG_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Layer = voxblox::Layer<Voxel> + Block<Voxel> + AnyIndexHash (Appendix A.2) */
+/* A voxel carries (distance, weight); observed <=> weight > 1e-6.            */
+/* For an ESDF layer upload weight = observed ? 1 : 0.                        */
+/* ------------------------------------------------------------------------- */
+typedef struct vgo_layer vgo_layer;
+
+vgo_layer* vgo_layer_create(float voxel_size, int voxels_per_side);
+void vgo_layer_destroy(vgo_layer* layer);
+/* Adds (or overwrites) a block. distance/weight may be NULL (zero-filled).
+ * Returns the block slot. */
+int vgo_layer_add_block(vgo_layer* layer, const int32_t idx[3], const float* distance,
+                        const float* weight);
+int vgo_layer_num_blocks(const vgo_layer* layer);
+int vgo_layer_find_block(const vgo_layer* layer, const int32_t idx[3]);
+/* Copies all blocks out in slot (= allocation) order. */
+void vgo_layer_export(const vgo_layer* layer, int32_t* idx, float* distance, float* weight);
+float vgo_layer_voxel_size_inv(const vgo_layer* layer);
+float vgo_layer_block_size_inv(const vgo_layer* layer);
+
+/* ------------------------------------------------------------------------- */
+/* Index math (voxblox/core/common.h, Appendix A.2)                           */
+/* ------------------------------------------------------------------------- */
+/* floor(p * inv + 1e-6) per axis, float arithmetic. */
+void vgo_grid_index_from_point(const float p[3], float grid_size_inv, int32_t out[3]);
+/* global voxel index -> (block index, local voxel index), upstream float/bitmask forms */
+void vgo_block_and_local_from_global(const int64_t g[3], int vps, int32_t block[3],
+                                     int32_t local[3]);
+
+/* ------------------------------------------------------------------------- */
+/* Interpolator<V>::getVoxelsAndQVector (voxblox interpolator_inl.h, A.3)     */
+/* ------------------------------------------------------------------------- */
+/* Returns 1 when all 8 neighbours exist and are observed. On success (and on
+ * failure as far as computed) fills: base block index, the 8 (slot, linear
+ * voxel index) pairs, the 8 distances and the q vector. */
+int vgo_interp_voxels_and_q(const vgo_layer* layer, const float pos[3], int32_t base_block[3],
+                            int32_t base_voxel[3], int32_t slots[8], int32_t linear[8],
+                            float distances[8], float q[8]);
+
+/* ------------------------------------------------------------------------- */
+/* minkindr QuatTransformationTemplate<float> (Appendix A.1)                  */
+/* T = [qw qx qy qz tx ty tz]                                                 */
+/* ------------------------------------------------------------------------- */
+void vgo_T_exp(const float v6[6], float T[7]);
+void vgo_T_inverse(const float T[7], float out[7]);
+void vgo_T_compose(const float A[7], const float B[7], float out[7]);
+void vgo_T_transform(const float T[7], const float p[3], float out[3]);
+
+/* ------------------------------------------------------------------------- */
+/* RegistrationCostFunction::Evaluate                                         */
+/* src/backend/constraint/cost_functions/registration_cost_function.cpp:58-298 */
+/* ------------------------------------------------------------------------- */
+/* points: n x {x,y,z}, distance[n], weight[n] (RegistrationPoint AoS split in 3 arrays).
+ * residuals: n doubles. jac_ref/jac_read: n x 4 row-major doubles, each may be NULL.
+ * Returns 1 (true) or 0 (false: summed weight == 0, cpp:273). Deterministic mode
+ * (sampling_ratio == -1) only. */
+int vgo_reg_evaluate(const vgo_layer* reading_layer, int n, const float* xyz,
+                     const float* distance, const float* weight, double no_correspondence_cost,
+                     const double ref_pose[4], const double read_pose[4], double* residuals,
+                     double* jac_ref, double* jac_read);
+
+/* The float pose-setup block of Evaluate (cpp:61-110): fills
+ * T_reading_reference [7] and {cos_e, sin_e, cos_emo, sin_emo, xe, ye, xo, yo}. */
+void vgo_reg_pose_setup(const double ref_pose[4], const double read_pose[4], float T_rr[7],
+                        float trig[8]);
+
+/* ------------------------------------------------------------------------- */
+/* RelativePoseCostFunction::operator()                                       */
+/* include/voxgraph/backend/constraint/cost_functions/relative_pose_cost_function_inl.h:8-70 */
+/* Jacobians are the analytic derivatives autodiff would produce.             */
+/* ------------------------------------------------------------------------- */
+void vgo_relpose_evaluate(const double pose_a[4], const double pose_b[4], const double t_obs[3],
+                          double yaw_obs, const double sqrt_info[16], double r[4],
+                          double jac_a[16], double jac_b[16]);
+/* Constraint ctor (src/backend/constraint/constraint.cpp:4-38): LLT lower factor.
+ * Returns 0 ok, -1 not positive definite. */
+int vgo_sqrt_information(const double info[16], double sqrt_info[16]);
+/* NormalizeAngle (include/voxgraph/backend/local_parameterization/normalize_angle.h:11-16) */
+double vgo_normalize_angle(double a);
+
+/* ------------------------------------------------------------------------- */
+/* Pose graph + Ceres-default Levenberg-Marquardt (pose_graph.cpp:85-106, A.6) */
+/* ------------------------------------------------------------------------- */
+typedef struct vgo_graph vgo_graph;
+
+typedef struct vgo_solver_options {
+  int max_num_iterations;        /* Ceres default 50 */
+  double parameter_tolerance;    /* pose_graph.cpp:93 -> 3e-3 (Ceres default 1e-8) */
+  double function_tolerance;     /* 1e-6 */
+  double gradient_tolerance;     /* 1e-10 */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;     /* 1e16 */
+  double min_trust_region_radius;     /* 1e-32 */
+  double min_relative_decrease;       /* 1e-3 */
+  double min_lm_diagonal;             /* 1e-6 */
+  double max_lm_diagonal;             /* 1e32 */
+  double max_solver_time_s;           /* pose_graph.cpp:95 -> 4 */
+  int jacobi_scaling;                 /* 1 */
+  int num_threads;                    /* pose_graph.cpp:96 -> 4 */
+  int exclude_registration;           /* PoseGraph::optimize(bool) */
+} vgo_solver_options;
+
+typedef struct vgo_solver_summary {
+  int iterations;            /* LM iterations performed (incl. unsuccessful) */
+  int num_successful_steps;
+  int num_residual_evals;    /* full-problem evaluations */
+  int termination;           /* 0 parameter tol, 1 function tol, 2 gradient tol,
+                                3 max iterations, 4 max time, 5 min radius, 6 failure */
+  double initial_cost, final_cost;
+  double total_time_s;
+  double eval_time_s;        /* time inside residual/Jacobian evaluation */
+  double linear_solver_time_s;
+} vgo_solver_summary;
+
+void vgo_solver_options_default(vgo_solver_options* o);
+
+vgo_graph* vgo_graph_create(void);
+void vgo_graph_destroy(vgo_graph* g);
+/* addSubmapNode (pose_graph.cpp:12-14). Returns node index. */
+int vgo_graph_add_node(vgo_graph* g, uint32_t id, const double xyzyaw[4], int constant);
+/* addRelativePoseConstraint (pose_graph.cpp:41-46). sqrt_info row-major 4x4. */
+int vgo_graph_add_relative(vgo_graph* g, uint32_t id_a, uint32_t id_b, const double t_obs[3],
+                           double yaw_obs, const double sqrt_info[16]);
+/* One registration residual block: reference points (not copied; caller keeps them
+ * alive) registered against reading layer. PoseGraph::addRegistrationConstraint's
+ * mirroring (pose_graph.cpp:63-71) is done by the caller. */
+int vgo_graph_add_registration(vgo_graph* g, uint32_t ref_id, uint32_t read_id,
+                               const vgo_layer* reading_layer, int n, const float* xyz,
+                               const float* distance, const float* weight,
+                               double no_correspondence_cost);
+void vgo_graph_reset_registration(vgo_graph* g);
+int vgo_graph_num_nodes(const vgo_graph* g);
+int vgo_graph_num_registration_residuals(const vgo_graph* g);
+void vgo_graph_get_poses(const vgo_graph* g, double* xyzyaw);
+void vgo_graph_set_poses(vgo_graph* g, const double* xyzyaw);
+
+/* Evaluates the whole problem at the current poses the way Ceres would:
+ * cost = 1/2 sum r^2, gradient g = J^T r (4 per node, node order), H = J^T J
+ * dense (4N x 4N row-major). Constant nodes are included in the layout (their
+ * rows/cols are simply what the Jacobians give); any output may be NULL.
+ * Returns 1 ok, 0 if some registration Evaluate returned false. */
+int vgo_graph_eval(vgo_graph* g, int num_threads, int exclude_registration, double* cost,
+                   double* gradient, double* H);
+/* Per-registration-constraint summed squared residual (pose_graph.cpp:194-207). */
+void vgo_graph_registration_costs(vgo_graph* g, double* per_constraint_sq_sum);
+
+int vgo_graph_solve(vgo_graph* g, const vgo_solver_options* opts, vgo_solver_summary* summary);
+
+/* ------------------------------------------------------------------------- */
+/* TSDF integration (voxblox tsdf_integrator.cc / integrator_utils, A.4)      */
+/* ------------------------------------------------------------------------- */
+typedef struct vgo_tsdf_config {
+  float default_truncation_distance; /* voxgraph_mapper.yaml:23 -> 0.6 */
+  float max_weight;                  /* 10000 */
+  int voxel_carving_enabled;         /* 1 */
+  float min_ray_length_m;            /* 0.1 */
+  float max_ray_length_m;            /* yaml:24 -> 16 */
+  int use_const_weight;              /* yaml:25 -> 1 */
+  int allow_clear;                   /* 1 */
+  int use_weight_dropoff;            /* yaml:26 -> 1 */
+  int use_sparsity_compensation_factor; /* yaml:27 -> 1 */
+  float sparsity_compensation_factor;   /* yaml:28 -> 20 */
+  /* FastTsdfIntegrator only */
+  float start_voxel_subsampling_factor; /* 2 */
+  int max_consecutive_ray_collisions;   /* 2 */
+  int mode;                             /* 0 = simple (every ray, every voxel), 1 = fast */
+} vgo_tsdf_config;
+
+typedef struct vgo_tsdf_stats {
+  int64_t rays_valid;      /* rays that passed isPointValid */
+  int64_t rays_cast;       /* rays actually cast (fast mode skips some) */
+  int64_t voxel_updates;   /* updateTsdfVoxel calls */
+  int64_t blocks_allocated;
+} vgo_tsdf_stats;
+
+void vgo_tsdf_config_default(vgo_tsdf_config* c);
+/* T_G_C = [qw qx qy qz tx ty tz]. Single-threaded, points in order. */
+void vgo_tsdf_integrate(vgo_layer* layer, const vgo_tsdf_config* cfg, const float T_G_C[7],
+                        int n, const float* points_C, vgo_tsdf_stats* stats);
+/* RayCaster restatement: writes up to max_out global voxel indices (int64 x 3);
+ * returns the number the caster emits. cast_from_origin=1 -> start->end. */
+int vgo_raycast(const float origin[3], const float point_G[3], int is_clearing,
+                int voxel_carving, float max_ray_length_m, float voxel_size_inv,
+                float truncation_distance, int cast_from_origin, int64_t* out, int max_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VG_ORACLE_H_ */
