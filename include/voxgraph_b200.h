@@ -1,0 +1,212 @@
+/*
+ * voxgraph_b200.h — C-ABI of the B200-native voxgraph hot paths.
+ *
+ * Drop-in boundary for (paths relative to /root/reference/voxgraph/):
+ *   b1  RegistrationCostFunction::Evaluate
+ *         include/voxgraph/backend/constraint/cost_functions/registration_cost_function.h:47-48
+ *         src/backend/constraint/cost_functions/registration_cost_function.cpp:58-298
+ *   b2  PoseGraph  (include/voxgraph/backend/pose_graph.h:21-55, src/backend/pose_graph.cpp)
+ *   b3  voxblox::TsdfIntegratorBase::integratePointCloud as driven by
+ *         PointcloudIntegrator::integratePointcloud
+ *         (src/frontend/measurement_processors/pointcloud_integrator.cpp:66-84)
+ *
+ * Conventions: plain pointers and sizes, caller owns every host buffer, the context
+ * owns all device memory, every function returns an int status (no exceptions or
+ * aborts cross the boundary; vgx_last_error() gives the message).  One context per
+ * GPU; a context is not thread-safe.  There is NO CPU fallback: every entry point
+ * needs a CUDA device and fails with VGX_ERR_CUDA without one.
+ */
+#ifndef VOXGRAPH_B200_H_
+#define VOXGRAPH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGX_OK 0
+#define VGX_ZERO_WEIGHT 1      /* Evaluate() would return false (cpp:273) */
+#define VGX_ERR_INVALID (-1)
+#define VGX_ERR_CUDA (-2)
+#define VGX_ERR_NOT_FOUND (-3)
+#define VGX_ERR_NOMEM (-4)
+#define VGX_ERR_NCCL (-5)
+#define VGX_ERR_CAPACITY (-6)
+
+typedef struct vgx_ctx vgx_ctx;
+
+/* ------------------------------------------------------------------ context */
+int vgx_device_count(void);
+int vgx_ctx_create(int device, vgx_ctx** out);
+void vgx_ctx_destroy(vgx_ctx* ctx);
+const char* vgx_last_error(const vgx_ctx* ctx);
+/* cudaStream_t all work of this context is enqueued on (for event timing). */
+void* vgx_ctx_stream(vgx_ctx* ctx);
+int vgx_ctx_synchronize(vgx_ctx* ctx);
+
+/* Kernel accounting: when enabled the library brackets each of its kernels with
+ * CUDA events on the context stream. which: 0 = registration reduce kernel,
+ * 1 = registration emit kernel, 2 = TSDF integrate kernel, 3 = TSDF allocate kernel,
+ * 4 = Cholesky/LM kernels, 5 = everything else. */
+int vgx_profile_enable(vgx_ctx* ctx, int on);
+int vgx_profile_reset(vgx_ctx* ctx);
+int vgx_profile_get(vgx_ctx* ctx, int which, double* total_ms, int64_t* launches);
+/* total kernels launched by the library since reset (counted even when disabled) */
+int64_t vgx_launch_count(vgx_ctx* ctx);
+
+/* ------------------------------------------------------------------ submaps */
+/* Replaces voxblox::Layer<TsdfVoxel|EsdfVoxel> + Block + block hash: dense 16^3 bricks
+ * in HBM behind a GPU open-addressing hash keyed on the voxblox block index.
+ * A voxel is (distance, weight); observed <=> weight > 1e-6 (upload an ESDF layer with
+ * weight = observed ? 1 : 0).  Voxel order inside a block: x + vps*(y + vps*z). */
+
+/* Upload a finished layer (replaces any previous content of submap_id). */
+int vgx_submap_upload(vgx_ctx* ctx, uint32_t submap_id, float voxel_size, int voxels_per_side,
+                      int n_blocks, const int32_t* block_idx /* n x 3 */,
+                      const float* distance /* n x vps^3 */,
+                      const float* weight /* n x vps^3 */);
+/* Create an empty (active) submap that vgx_tsdf_integrate fills. */
+int vgx_submap_create(vgx_ctx* ctx, uint32_t submap_id, float voxel_size, int voxels_per_side,
+                      int capacity_blocks);
+/* VoxgraphSubmap::finishSubmap (voxgraph_submap.cpp:84-107), device part: freezes the
+ * layer and builds the registration view of the bricks. */
+int vgx_submap_finish(vgx_ctx* ctx, uint32_t submap_id);
+int vgx_submap_free(vgx_ctx* ctx, uint32_t submap_id);
+int vgx_submap_block_count(vgx_ctx* ctx, uint32_t submap_id, int* n_blocks);
+/* Copies blocks back in allocation order (parity checks / saving). */
+int vgx_submap_download(vgx_ctx* ctx, uint32_t submap_id, int max_blocks, int32_t* block_idx,
+                        float* distance, float* weight, int* n_blocks);
+
+/* Registration points of a submap = WeightedSampler<RegistrationPoint> items
+ * (include/voxgraph/frontend/submap_collection/registration_point.h:6-12).
+ * point_type: 0 = kVoxels, 1 = kIsosurfacePoints (voxgraph_submap.h RegistrationPointType). */
+#define VGX_POINTS_VOXELS 0
+#define VGX_POINTS_ISOSURFACE 1
+int vgx_submap_upload_points(vgx_ctx* ctx, uint32_t submap_id, int point_type, int n,
+                             const float* xyz /* n x 3 */, const float* distance,
+                             const float* weight);
+
+/* ------------------------------------------------------------------ b3: TSDF integration */
+typedef struct vgx_tsdf_config {          /* voxblox::TsdfIntegratorBase::Config */
+  float default_truncation_distance;      /* voxgraph_mapper.yaml:23  0.6 */
+  float max_weight;                       /* 10000 */
+  int voxel_carving_enabled;              /* 1 */
+  float min_ray_length_m;                 /* 0.1 */
+  float max_ray_length_m;                 /* yaml:24  16 */
+  int use_const_weight;                   /* yaml:25  1 */
+  int allow_clear;                        /* 1 */
+  int use_weight_dropoff;                 /* yaml:26  1 */
+  int use_sparsity_compensation_factor;   /* yaml:27  1 */
+  float sparsity_compensation_factor;     /* yaml:28  20 */
+  float start_voxel_subsampling_factor;   /* FastTsdfIntegrator, 2 */
+  int max_consecutive_ray_collisions;     /* FastTsdfIntegrator, 2 */
+  int mode;                               /* 0 simple (every ray, every voxel), 1 fast */
+} vgx_tsdf_config;
+
+typedef struct vgx_tsdf_stats {
+  int64_t rays_valid;
+  int64_t rays_cast;
+  int64_t voxel_updates;
+  int64_t blocks_allocated;
+} vgx_tsdf_stats;
+
+void vgx_tsdf_config_default(vgx_tsdf_config* cfg);
+/* integratePointCloud(T_G_C, points_C, colors): T_G_C = [qw qx qy qz tx ty tz];
+ * rgba may be NULL. Host buffers; copies are part of the call. */
+int vgx_tsdf_integrate(vgx_ctx* ctx, uint32_t submap_id, const float T_G_C[7], int n,
+                       const float* points_C /* n x 3 */, const uint8_t* rgba /* n x 4 or NULL */,
+                       const vgx_tsdf_config* cfg, vgx_tsdf_stats* stats /* may be NULL */);
+
+/* ------------------------------------------------------------------ b1: cost function */
+typedef struct vgx_reg_config {           /* RegistrationCostFunction::Config (h:17-41) */
+  int registration_point_type;            /* VGX_POINTS_* ; default isosurface */
+  double no_correspondence_cost;          /* 0 */
+  float sampling_ratio;                   /* -1 (only the deterministic mode is supported) */
+} vgx_reg_config;
+void vgx_reg_config_default(vgx_reg_config* cfg);
+
+/* Number of residuals of the (reference -> reading) cost function (cpp:45-55). */
+int vgx_reg_num_residuals(vgx_ctx* ctx, uint32_t reference_submap_id, const vgx_reg_config* cfg,
+                          int* num_residuals);
+/* Evaluate(parameters, residuals, jacobians): Ceres layout, residuals[K] and two K x 4
+ * row-major Jacobian blocks (either may be NULL). Returns VGX_OK, or VGX_ZERO_WEIGHT
+ * where Evaluate returns false. */
+int vgx_reg_eval_emit(vgx_ctx* ctx, uint32_t reference_submap_id, uint32_t reading_submap_id,
+                      const vgx_reg_config* cfg, const double reference_pose[4],
+                      const double reading_pose[4], double* residuals, double* jac_reference,
+                      double* jac_reading);
+
+/* ------------------------------------------------------------------ b2: pose graph */
+/* addSubmapNode for every node (replaces the node set). xyzyaw: n x 4 [x,y,z,yaw]. */
+int vgx_graph_set_nodes(vgx_ctx* ctx, int n, const uint32_t* submap_ids, const double* xyzyaw,
+                        const uint8_t* constant);
+int vgx_graph_set_poses(vgx_ctx* ctx, const double* xyzyaw);
+int vgx_graph_get_poses(vgx_ctx* ctx, double* xyzyaw);
+/* add{Relative,Absolute}PoseConstraint: m edges, observed [tx,ty,tz,yaw], sqrt-information
+ * (lower LLT factor, row-major 4x4, constraint.cpp:8-14). */
+int vgx_graph_set_relative_edges(vgx_ctx* ctx, int m, const uint32_t* ids_a, const uint32_t* ids_b,
+                                 const double* t_obs_xyzyaw, const double* sqrt_info);
+/* One entry per registration residual block (reference -> reading). The caller adds the
+ * mirrored block for isosurface points as PoseGraph::addRegistrationConstraint does
+ * (pose_graph.cpp:63-71). Replaces the previous list (resetRegistrationConstraints). */
+int vgx_graph_set_registration_constraints(vgx_ctx* ctx, int p, const uint32_t* reference_ids,
+                                           const uint32_t* reading_ids, const vgx_reg_config* cfg);
+int vgx_graph_num_registration_residuals(vgx_ctx* ctx, int64_t* local, int64_t* global);
+
+/* Whole-problem evaluation at the current poses, fused on the device: cost = 1/2 sum r^2,
+ * gradient = J^T r (4 per node), H = J^T J (dense 4N x 4N row-major). Outputs may be NULL.
+ * With a communicator the result is the all-reduced global one. */
+int vgx_graph_eval(vgx_ctx* ctx, int exclude_registration, double* cost, double* gradient,
+                   double* H);
+/* Enqueue only (no device->host copy, no sync): for device-side timing. */
+int vgx_graph_eval_async(vgx_ctx* ctx, int exclude_registration);
+/* Sum of squared residuals per registration constraint (pose_graph.cpp:194-207). */
+int vgx_graph_registration_costs(vgx_ctx* ctx, double* per_constraint);
+
+typedef struct vgx_solver_options {       /* ceres::Solver::Options subset, pose_graph.cpp:91-97 */
+  int max_num_iterations;                 /* 50 */
+  double parameter_tolerance;             /* 3e-3 */
+  double function_tolerance;              /* 1e-6 */
+  double gradient_tolerance;              /* 1e-10 */
+  double initial_trust_region_radius;     /* 1e4 */
+  double max_trust_region_radius;         /* 1e16 */
+  double min_trust_region_radius;         /* 1e-32 */
+  double min_relative_decrease;           /* 1e-3 */
+  double min_lm_diagonal;                 /* 1e-6 */
+  double max_lm_diagonal;                 /* 1e32 */
+  double max_solver_time_s;               /* 4 */
+  int jacobi_scaling;                     /* 1 */
+  int exclude_registration;               /* PoseGraph::optimize(bool) */
+} vgx_solver_options;
+
+typedef struct vgx_solver_summary {       /* what voxgraph reads off ceres::Solver::Summary */
+  int iterations;
+  int num_successful_steps;
+  int num_residual_evals;
+  int termination;  /* 0 parameter tol, 1 function tol, 2 gradient tol, 3 max iterations,
+                       4 max time, 5 min radius, 6 failure */
+  double initial_cost, final_cost;
+  double total_time_s;
+} vgx_solver_summary;
+
+void vgx_solver_options_default(vgx_solver_options* o);
+/* PoseGraph::optimize: Levenberg-Marquardt with Ceres' default trust-region schedule,
+ * device resident; optimised poses are written to xyzyaw_out (n x 4, may be NULL) and
+ * stay the graph's current poses. */
+int vgx_graph_solve(vgx_ctx* ctx, const vgx_solver_options* opts, double* xyzyaw_out,
+                    vgx_solver_summary* summary);
+
+/* ------------------------------------------------------------------ multi-GPU */
+/* One process per GPU. Registration constraints are sharded over the ranks of the
+ * communicator (every rank passes the same full list and holds the submaps it needs);
+ * the per-node / per-edge normal-equation blocks are summed with one ncclAllReduce per
+ * evaluation. */
+int vgx_comm_unique_id(uint8_t id[128]);
+int vgx_comm_init(vgx_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
+int vgx_comm_destroy(vgx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXGRAPH_B200_H_ */

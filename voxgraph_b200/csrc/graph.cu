@@ -1,0 +1,1093 @@
+// Pose graph on the device: fused evaluation of all residual blocks into packed
+// normal-equation blocks, NCCL all-reduce across ranks, and a device-resident
+// Levenberg-Marquardt with Ceres' default trust-region schedule.
+//
+// Reference: voxgraph/src/backend/pose_graph.cpp:48-106 (constraints, optimize()),
+// include/voxgraph/backend/constraint/cost_functions/relative_pose_cost_function_inl.h:8-70,
+// src/backend/node/node_collection.cpp:8-12 (x,y,z additive, yaw wrapped),
+// Ceres 1.x TrustRegionMinimizer/LevenbergMarquardtStrategy defaults.
+#include <math.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <new>
+#include <numeric>
+
+#include "registration.cuh"
+#include "registration_kernels.h"
+
+#define BLK_STRIDE 80   // 64 (J^T J of the residual block, 8x8) + 8 (J^T r) + 1 (sum r^2) + pad
+#define PACK_HDR 4      // [0] cost, [1..3] reserved
+
+struct LmState {
+  double radius, decrease_factor;
+  double cost, cand_cost, model_cost_change;
+  double x_norm, step_norm, gmax;
+  int reuse_diagonal, consecutive_invalid;
+  int iterations, successful, evals;
+  int termination, done, accepted, step_valid, scale_ready;
+};
+
+struct LmOpts {
+  int max_num_iterations;
+  double parameter_tolerance, function_tolerance, gradient_tolerance;
+  double max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  int jacobi_scaling;
+};
+
+struct VgxGraph {
+  int N = 0;
+  std::vector<uint32_t> ids;
+  std::vector<double> x;
+  std::vector<uint8_t> constant;
+  std::map<uint32_t, int> index;
+  std::vector<VgxRelEdge> rel;
+  std::vector<uint32_t> reg_ref, reg_read;
+  vgx_reg_config reg_cfg;
+  bool dirty = true;
+
+  // derived
+  std::vector<int> local;  // global indices of this rank's registration constraints
+  std::vector<int> block_nodes;  // E x 2 (host copy)
+  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_blk = 0;
+  int E = 0;               // off-diagonal blocks
+  int n_free = 0;          // reduced dimension 4 * (non-constant nodes)
+  int64_t residuals_local = 0, residuals_global = 0;
+  bool zero_weight = false;
+  size_t packed_len = 0;
+
+  // device
+  RegConstraintDev* d_cons = nullptr;
+  RegPoseConst* d_poses = nullptr;
+  RegTile* d_tiles = nullptr;
+  int* d_tile_begin = nullptr;
+  double* d_partials = nullptr;
+  double* d_csum = nullptr;
+  VgxRelEdge* d_rel = nullptr;
+  double* d_blk = nullptr;
+  int* d_csr_begin = nullptr;   // N + E + 1
+  int2* d_csr_items = nullptr;  // (blk, role)
+  int* d_block_nodes = nullptr; // E x 2
+  int* d_red_offset = nullptr;  // N: reduced offset or -1
+  double* d_x = nullptr;
+  double* d_xc = nullptr;
+  double* d_packed[2] = {nullptr, nullptr};
+  double* d_A = nullptr;
+  double* d_scale = nullptr;
+  double* d_diag = nullptr;
+  double* d_gs = nullptr;
+  double* d_step = nullptr;
+  LmState* d_state = nullptr;
+  LmState* h_state = nullptr;
+};
+
+static void free_tables(VgxGraph* g) {
+  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin);
+  cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_blk);
+  cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
+  cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
+  cudaFree(g->d_packed[0]); cudaFree(g->d_packed[1]);
+  cudaFree(g->d_A); cudaFree(g->d_scale); cudaFree(g->d_diag); cudaFree(g->d_gs); cudaFree(g->d_step);
+  cudaFree(g->d_state);
+  if (g->h_state) cudaFreeHost(g->h_state);
+  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr;
+  g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_blk = nullptr;
+  g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
+  g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
+  g->d_packed[0] = g->d_packed[1] = nullptr;
+  g->d_A = nullptr; g->d_scale = nullptr; g->d_diag = nullptr; g->d_gs = nullptr; g->d_step = nullptr;
+  g->d_state = nullptr; g->h_state = nullptr;
+}
+
+void vgx_graph_free(vgx_ctx* c) {
+  if (!c->graph) return;
+  free_tables(c->graph);
+  delete c->graph;
+  c->graph = nullptr;
+}
+
+void vgx_graph_invalidate_registration(vgx_ctx* c) {
+  if (c->graph) c->graph->dirty = true;
+}
+
+static VgxGraph* graph_of(vgx_ctx* c) {
+  if (!c->graph) {
+    c->graph = new (std::nothrow) VgxGraph();
+    if (c->graph) vgx_reg_config_default(&c->graph->reg_cfg);
+  }
+  return c->graph;
+}
+
+// ------------------------------------------------------------------ kernels: blocks
+__device__ __forceinline__ double normalize_angle(double a) {
+  const double two_pi = 6.283185307179586476925286766559;
+  return a - two_pi * floor((a + 3.14159265358979323846) / two_pi);
+}
+
+// RelativePoseCostFunction (inl.h:8-70) with the analytic Jacobians autodiff yields.
+__global__ void rel_blocks_kernel(const VgxRelEdge* __restrict__ edges, const double* __restrict__ x,
+                                  double* __restrict__ blk, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const VgxRelEdge E = edges[e];
+  const double* A = x + 4 * E.a;
+  const double* B = x + 4 * E.b;
+  const double c = cos(A[3]), s = sin(A[3]);
+  const double dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
+  double err[4];
+  err[0] = (c * dx + s * dy) - E.t_obs[0];
+  err[1] = (-s * dx + c * dy) - E.t_obs[1];
+  err[2] = dz - E.t_obs[2];
+  err[3] = normalize_angle((B[3] - A[3]) - E.yaw_obs);
+  const double ja[16] = {-c, -s, 0, -s * dx + c * dy, s, -c, 0, -c * dx - s * dy,
+                         0, 0, -1, 0, 0, 0, 0, -1};
+  const double jb[16] = {c, s, 0, 0, -s, c, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double r[4], J[4][8];
+  for (int i = 0; i < 4; ++i) {
+    double acc = 0;
+    for (int k = 0; k < 4; ++k) acc += E.L[4 * i + k] * err[k];
+    r[i] = acc;
+    for (int j = 0; j < 4; ++j) {
+      double sa = 0, sb = 0;
+      for (int k = 0; k < 4; ++k) {
+        sa += E.L[4 * i + k] * ja[4 * k + j];
+        sb += E.L[4 * i + k] * jb[4 * k + j];
+      }
+      J[i][j] = sa;
+      J[i][4 + j] = sb;
+    }
+  }
+  double* o = blk + (size_t)e * BLK_STRIDE;
+  for (int a = 0; a < 8; ++a) {
+    for (int b = 0; b < 8; ++b) {
+      double h = 0;
+      for (int i = 0; i < 4; ++i) h += J[i][a] * J[i][b];
+      o[8 * a + b] = h;
+    }
+    double g = 0;
+    for (int i = 0; i < 4; ++i) g += J[i][a] * r[i];
+    o[64 + a] = g;
+  }
+  o[72] = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+}
+
+// csum (21 sums of j = (jr0..jr3, je3)) -> 8x8 block of the residual block.
+__global__ void reg_expand_kernel(const double* __restrict__ csum, double* __restrict__ blk,
+                                  int n, int zero) {
+  const int c = blockIdx.x;
+  const int t = threadIdx.x;  // 0..79
+  if (c >= n || t >= 73) return;
+  const double* s = csum + (size_t)c * VGX_REG_NSTRIDE;
+  double* o = blk + (size_t)c * BLK_STRIDE;
+  if (zero) { o[t] = 0.0; return; }
+  const int m[8] = {0, 1, 2, 3, 0, 1, 2, 4};
+  const double sg[8] = {1, 1, 1, 1, -1, -1, -1, 1};
+  if (t < 64) {
+    const int a = t >> 3, b = t & 7;
+    int p = m[a], q = m[b];
+    if (p > q) { int tmp = p; p = q; q = tmp; }
+    const int idx = p * 5 - (p * (p - 1)) / 2 + (q - p);
+    o[t] = sg[a] * sg[b] * s[idx];
+  } else if (t < 72) {
+    const int a = t - 64;
+    o[t] = sg[a] * s[15 + m[a]];
+  } else {
+    o[72] = s[20];
+  }
+}
+
+// One warp per output block: lanes 0..15 the 4x4 entries, lanes 16..19 the gradient
+// (diagonal blocks only). Items are summed in list order -> bit-reproducible.
+__global__ void assemble_kernel(const double* __restrict__ blk, const int* __restrict__ csr_begin,
+                                const int2* __restrict__ items, double* __restrict__ packed, int N,
+                                int E) {
+  const int ob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ob >= N + E) return;
+  const int i0 = csr_begin[ob], i1 = csr_begin[ob + 1];
+  double acc = 0;
+  const bool diag = ob < N;
+  if (lane < 16) {
+    const int r = lane >> 2, cc = lane & 3;
+    for (int i = i0; i < i1; ++i) {
+      const int2 it = items[i];
+      const double* b = blk + (size_t)it.x * BLK_STRIDE;
+      int row, col;
+      switch (it.y) {
+        case 0: row = r; col = cc; break;           // A-A
+        case 1: row = 4 + r; col = 4 + cc; break;   // B-B
+        case 2: row = r; col = 4 + cc; break;       // A rows, B cols
+        default: row = 4 + r; col = cc; break;      // B rows, A cols
+      }
+      acc += b[8 * row + col];
+    }
+    double* out = packed + PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob;
+    out[lane] = acc;
+  } else if (lane < 20 && diag) {
+    const int r = lane - 16;
+    for (int i = i0; i < i1; ++i) {
+      const int2 it = items[i];
+      const double* b = blk + (size_t)it.x * BLK_STRIDE;
+      acc += b[64 + (it.y == 0 ? r : 4 + r)];
+    }
+    packed[PACK_HDR + 4 * (size_t)ob + r] = acc;
+  }
+}
+
+// cost = 1/2 sum over blocks of sum r^2, fixed-order tree.
+__global__ void cost_kernel(const double* __restrict__ blk, int n_blk, double* __restrict__ packed) {
+  __shared__ double s[256];
+  double a = 0;
+  for (int i = threadIdx.x; i < n_blk; i += 256) a += blk[(size_t)i * BLK_STRIDE + 72];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    packed[0] = 0.5 * s[0];
+    packed[1] = 0; packed[2] = 0; packed[3] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ kernels: LM
+// Reduced, Jacobi-scaled normal matrix, lower triangle, column-major with leading
+// dimension M = n + 1; row n carries the scaled gradient (forward substitution for free).
+__global__ void lm_build_kernel(const double* __restrict__ packed, const int* __restrict__ red,
+                                const int* __restrict__ block_nodes, int N, int E, int n,
+                                double* __restrict__ A, double* __restrict__ scale,
+                                double* __restrict__ diag, double* __restrict__ gs,
+                                LmState* __restrict__ st, LmOpts o) {
+  const int M = n + 1;
+  const double* g = packed + PACK_HDR;
+  const double* D = packed + PACK_HDR + 4 * (size_t)N;
+  const double* O = D + 16 * (size_t)N;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  const bool first = st->scale_ready == 0;
+  const bool reuse = st->reuse_diagonal != 0;
+  const double radius = st->radius;
+  // scale from the first Jacobian's column norms (TrustRegionMinimizer, iteration 0)
+  auto sc = [&](int node, int k) -> double {
+    if (!o.jacobi_scaling) return 1.0;
+    if (first) return 1.0 / (1.0 + sqrt(D[16 * (size_t)node + 5 * k]));
+    return scale[red[node] + k];
+  };
+  // diagonal blocks
+  for (int t = tid; t < N * 16; t += stride) {
+    const int node = t >> 4, r = (t >> 2) & 3, c = t & 3;
+    const int off = red[node];
+    if (off < 0 || r < c) continue;
+    const double sr = sc(node, r), scc = sc(node, c);
+    double v = sr * scc * D[16 * (size_t)node + 4 * r + c];
+    if (r == c) {
+      double d;
+      if (reuse) d = diag[off + r];
+      else d = fmin(fmax(v, o.min_lm_diagonal), o.max_lm_diagonal);
+      // lm_diagonal = sqrt(diag / radius); added squared
+      const double lm = sqrt(d / radius);
+      v += lm * lm;
+    }
+    A[(size_t)(off + c) * M + off + r] = v;
+  }
+  // off-diagonal blocks: rows = node i (smaller index), cols = node j
+  for (int t = tid; t < E * 16; t += stride) {
+    const int b = t >> 4, r = (t >> 2) & 3, c = t & 3;
+    const int ni = block_nodes[2 * b], nj = block_nodes[2 * b + 1];
+    const int oi = red[ni], oj = red[nj];
+    if (oi < 0 || oj < 0) continue;
+    const double v = sc(ni, r) * sc(nj, c) * O[16 * (size_t)b + 4 * r + c];
+    // lower triangle: row index must be the larger one (oj > oi because nj > ni)
+    A[(size_t)(oi + r) * M + (oj + c)] = v;
+  }
+  // gradient row + bookkeeping vectors
+  for (int t = tid; t < N * 4; t += stride) {
+    const int node = t >> 2, k = t & 3;
+    const int off = red[node];
+    if (off < 0) continue;
+    const double s = sc(node, k);
+    const double gsv = s * g[4 * node + k];
+    A[(size_t)(off + k) * M + n] = gsv;
+    gs[off + k] = gsv;
+  }
+}
+
+// Second pass (after lm_build): persist scale / diag. Separate so every thread of
+// lm_build sees the old values.
+__global__ void lm_persist_kernel(const double* __restrict__ packed, const int* __restrict__ red,
+                                  int N, double* __restrict__ scale, double* __restrict__ diag,
+                                  LmState* __restrict__ st, LmOpts o) {
+  const double* D = packed + PACK_HDR + 4 * (size_t)N;
+  const bool first = st->scale_ready == 0;
+  const bool reuse = st->reuse_diagonal != 0;
+  for (int t = threadIdx.x; t < N * 4; t += blockDim.x) {
+    const int node = t >> 2, k = t & 3;
+    const int off = red[node];
+    if (off < 0) continue;
+    double s = 1.0;
+    if (o.jacobi_scaling) s = first ? 1.0 / (1.0 + sqrt(D[16 * (size_t)node + 5 * k])) : scale[off + k];
+    if (first) scale[off + k] = s;
+    if (!reuse) {
+      const double v = s * s * D[16 * (size_t)node + 5 * k];
+      diag[off + k] = fmin(fmax(v, o.min_lm_diagonal), o.max_lm_diagonal);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st->scale_ready = 1;
+}
+
+// Blocked right-looking Cholesky of the (n+1) x (n+1) lower-triangular system, one CTA.
+// smem: sD[32][33] diagonal block, sP[(M - 32)][33] panel.
+#define CH_NB 32
+__global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int n,
+                                                    LmState* __restrict__ st) {
+  extern __shared__ double smem[];
+  double* sD = smem;                 // 32 x 33
+  double* sP = smem + CH_NB * 33;    // rows x 33
+  const int M = n + 1;
+  const int tid = threadIdx.x, T = blockDim.x;
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += CH_NB) {
+    const int nb = min(CH_NB, n - j0);
+    // 1. diagonal block -> smem
+    for (int t = tid; t < nb * nb; t += T) {
+      const int r = t % nb, c = t / nb;
+      if (r >= c) sD[r * 33 + c] = A[(size_t)(j0 + c) * M + j0 + r];
+    }
+    __syncthreads();
+    // 2. factor it (warp 0, lane = row)
+    if (tid < 32) {
+      const int r = tid;
+      for (int k = 0; k < nb; ++k) {
+        double d = sD[k * 33 + k];
+        if (!(d > 0.0) || !isfinite(d)) { if (r == 0) s_fail = 1; d = 1.0; }
+        const double sq = sqrt(d);
+        __syncwarp();
+        if (r == k) sD[k * 33 + k] = sq;
+        if (r > k && r < nb) sD[r * 33 + k] /= sq;
+        __syncwarp();
+        if (r > k && r < nb) {
+          const double lrk = sD[r * 33 + k];
+          for (int c = k + 1; c <= r; ++c) sD[r * 33 + c] -= lrk * sD[c * 33 + k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // write the factored diagonal block back
+    for (int t = tid; t < nb * nb; t += T) {
+      const int r = t % nb, c = t / nb;
+      if (r >= c) A[(size_t)(j0 + c) * M + j0 + r] = sD[r * 33 + c];
+    }
+    // 3. panel solve, one thread per row below the block (includes the rhs row n)
+    const int r0 = j0 + nb;
+    const int rows = M - r0;
+    for (int rr = tid; rr < rows; rr += T) {
+      double* p = sP + (size_t)rr * 33;
+      for (int c = 0; c < nb; ++c) {
+        double v = A[(size_t)(j0 + c) * M + r0 + rr];
+        for (int k = 0; k < c; ++k) v -= p[k] * sD[c * 33 + k];
+        v /= sD[c * 33 + c];
+        p[c] = v;
+        A[(size_t)(j0 + c) * M + r0 + rr] = v;
+      }
+    }
+    __syncthreads();
+    // 4. trailing update: A[i][j] -= sum_k P[i][k] P[j][k], i >= j, columns r0..n-1
+    const int tc = n - r0;  // trailing columns
+    if (tc > 0) {
+      // element (ri, cj) with cj in [0,tc), ri in [cj, rows)
+      const long long total = (long long)tc * rows - (long long)tc * (tc - 1) / 2;
+      // enumerate column by column so consecutive threads share the column
+      int cj = 0;
+      long long base = 0;  // elements before column cj
+      for (long long t = tid; t < total; t += T) {
+        while (t >= base + (rows - cj)) { base += rows - cj; ++cj; }
+        const int ri = cj + (int)(t - base);
+        const double* pi = sP + (size_t)ri * 33;
+        const double* pj = sP + (size_t)cj * 33;
+        double acc = 0;
+#pragma unroll 8
+        for (int k = 0; k < CH_NB; ++k) acc = fma(pi[k], pj[k], acc);
+        // nb < 32 only happens in the last panel, where tc == 0
+        A[(size_t)(r0 + cj) * M + r0 + ri] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && s_fail) st->step_valid = 0;
+}
+
+// Back substitution L^T x = y (y = row n of L), step = -x, model cost change, candidate.
+__global__ void __launch_bounds__(1024)
+lm_step_kernel(const double* __restrict__ A, int n, int N, const int* __restrict__ red,
+               const double* __restrict__ scale, const double* __restrict__ diag,
+               const double* __restrict__ gs, const double* __restrict__ x,
+               double* __restrict__ xc, double* __restrict__ step, LmState* __restrict__ st) {
+  extern __shared__ double sy[];  // n
+  __shared__ double s_red[3][32];
+  const int M = n + 1;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  for (int i = tid; i < n; i += T) sy[i] = A[(size_t)i * M + n];
+  __syncthreads();
+  const int nblk = (n + CH_NB - 1) / CH_NB;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int j0 = b * CH_NB, nb = min(CH_NB, n - j0);
+    // solve the nb x nb upper-triangular block (warp 0)
+    if (warp == 0) {
+      for (int k = nb - 1; k >= 0; --k) {
+        const double xk = sy[j0 + k] / A[(size_t)(j0 + k) * M + j0 + k];
+        __syncwarp();
+        if (lane == 0) sy[j0 + k] = xk;
+        if (lane < k) sy[j0 + lane] -= A[(size_t)(j0 + lane) * M + j0 + k] * xk;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // y_i -= sum_k L[j0+k][i] x_k for i < j0: one warp per column i, lanes over k
+    for (int i = warp; i < j0; i += nw) {
+      double v = (lane < nb) ? A[(size_t)i * M + j0 + lane] * sy[j0 + lane] : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) sy[i] -= v;
+    }
+    __syncthreads();
+  }
+  // step = -x ; model_cost_change = 1/2 sum x_i (gs_i + D_i x_i), D = diag / radius
+  const double radius = st->radius;
+  double mcc = 0;
+  int bad = 0;
+  for (int i = tid; i < n; i += T) {
+    const double xi = sy[i];
+    if (!isfinite(xi)) bad = 1;
+    step[i] = -xi;
+    mcc += 0.5 * xi * (gs[i] + (diag[i] / radius) * xi);
+  }
+  // candidate = Plus(x, step .* scale)
+  double sn2 = 0, xn2 = 0;
+  for (int t = tid; t < 4 * N; t += T) {
+    const int node = t >> 2, k = t & 3;
+    const int off = red[node];
+    const double xv = x[t];
+    double cv = xv;
+    if (off >= 0) {
+      const double d = -sy[off + k] * scale[off + k];
+      cv = (k == 3) ? normalize_angle(xv + d) : xv + d;
+      const double dd = xv - cv;
+      sn2 += dd * dd;
+      xn2 += xv * xv;
+    }
+    xc[t] = cv;
+  }
+  // block reduce (fixed order)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mcc += __shfl_xor_sync(0xffffffffu, mcc, off);
+    sn2 += __shfl_xor_sync(0xffffffffu, sn2, off);
+    xn2 += __shfl_xor_sync(0xffffffffu, xn2, off);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  if (lane == 0) { s_red[0][warp] = mcc; s_red[1][warp] = sn2; s_red[2][warp] = xn2; if (bad) atomicOr(&s_bad, 1); }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, b2 = 0, c2 = 0;
+    for (int w = 0; w < nw; ++w) { a += s_red[0][w]; b2 += s_red[1][w]; c2 += s_red[2][w]; }
+    st->model_cost_change = a;
+    st->step_norm = sqrt(b2);
+    st->x_norm = sqrt(c2);
+    if (s_bad || !(a > 0.0)) st->step_valid = 0;
+  }
+}
+
+// Accept / reject and termination tests of TrustRegionMinimizer (A.6).
+__global__ void lm_decide_kernel(const double* __restrict__ packed_cur,
+                                 const double* __restrict__ packed_cand,
+                                 const int* __restrict__ red, int N, double* __restrict__ x,
+                                 const double* __restrict__ xc, LmState* __restrict__ st, LmOpts o,
+                                 int cand_eval_ok) {
+  __shared__ double s_g[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // gradient max norm at the candidate (used if accepted)
+  double gm = 0;
+  for (int t = tid; t < 4 * N; t += blockDim.x)
+    if (red[t >> 2] >= 0) gm = fmax(gm, fabs(packed_cand[PACK_HDR + t]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, off));
+  if (lane == 0) s_g[warp] = gm;
+  __syncthreads();
+  __shared__ int s_accept;
+  if (tid == 0) {
+    gm = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) gm = fmax(gm, s_g[w]);
+    LmState S = *st;
+    S.accepted = 0;
+    S.iterations++;
+    const double cost = packed_cur[0];
+    const double cand = packed_cand[0];
+    S.cost = cost;
+    S.cand_cost = cand;
+    bool invalid = (S.step_valid == 0);
+    if (!invalid) { S.evals++; if (!cand_eval_ok) invalid = true; }
+    if (invalid) {
+      // HandleInvalidStep
+      if (++S.consecutive_invalid >= 5) { S.termination = 6; S.done = 1; }
+      S.radius /= S.decrease_factor; S.decrease_factor *= 2; S.reuse_diagonal = 1;
+    } else {
+      S.consecutive_invalid = 0;
+      if (S.step_norm <= o.parameter_tolerance * (S.x_norm + o.parameter_tolerance)) {
+        S.termination = 0; S.done = 1;  // ParameterToleranceReached (x is not updated)
+      } else {
+        const double cost_change = cost - cand;
+        if (fabs(cost_change) <= o.function_tolerance * cost) {
+          S.termination = 1; S.done = 1;  // FunctionToleranceReached
+        } else {
+          const double rel = cost_change / S.model_cost_change;
+          if (rel > o.min_relative_decrease) {
+            S.accepted = 1; S.successful++;
+            S.cost = cand;
+            S.gmax = gm;
+            const double q = 2.0 * rel - 1.0;
+            S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+            S.radius = fmin(o.max_radius, S.radius);
+            S.decrease_factor = 2.0; S.reuse_diagonal = 0;
+          } else {
+            S.radius /= S.decrease_factor; S.decrease_factor *= 2; S.reuse_diagonal = 1;
+          }
+        }
+      }
+    }
+    if (!S.done) {
+      // FinalizeIterationAndCheckIfMinimizerCanContinue for the next iteration
+      if (S.iterations >= o.max_num_iterations) { S.termination = 3; S.done = 1; }
+      else if (S.gmax <= o.gradient_tolerance) { S.termination = 2; S.done = 1; }
+      else if (S.radius <= o.min_radius) { S.termination = 5; S.done = 1; }
+    }
+    S.step_valid = 1;
+    s_accept = S.accepted;
+    *st = S;
+  }
+  __syncthreads();
+  if (s_accept)
+    for (int t = tid; t < 4 * N; t += blockDim.x) x[t] = xc[t];
+}
+
+__global__ void lm_init_kernel(const double* __restrict__ packed, const int* __restrict__ red, int N,
+                               LmState* __restrict__ st, double radius, LmOpts o) {
+  __shared__ double s_g[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double gm = 0;
+  for (int t = tid; t < 4 * N; t += blockDim.x)
+    if (red[t >> 2] >= 0) gm = fmax(gm, fabs(packed[PACK_HDR + t]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, off));
+  if (lane == 0) s_g[warp] = gm;
+  __syncthreads();
+  if (tid == 0) {
+    gm = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) gm = fmax(gm, s_g[w]);
+    LmState S;
+    memset(&S, 0, sizeof(S));
+    S.radius = radius; S.decrease_factor = 2.0;
+    S.cost = packed[0];
+    S.gmax = gm;
+    S.evals = 1;
+    S.step_valid = 1;
+    S.termination = 3;
+    if (o.max_num_iterations <= 0) { S.termination = 3; S.done = 1; }
+    else if (gm <= o.gradient_tolerance) { S.termination = 2; S.done = 1; }
+    *st = S;
+  }
+}
+
+// ------------------------------------------------------------------ table construction
+template <class T>
+static cudaError_t upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t st) {
+  *dptr = nullptr;
+  const size_t bytes = sizeof(T) * std::max<size_t>(v.size(), 1);
+  cudaError_t e = cudaMalloc((void**)dptr, bytes);
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpyAsync(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st);
+  return e;
+}
+
+static int build_tables(vgx_ctx* c, VgxGraph* g) {
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_tables(g);
+  const int N = g->N;
+  const int P = (int)g->reg_ref.size();
+  // ---- shard registration constraints over ranks: greedy by descending point count
+  std::vector<RegConstraintDev> all(P);
+  g->zero_weight = false;
+  g->residuals_global = 0;
+  for (int i = 0; i < P; ++i) {
+    int rc = vgx_fill_constraint(c, g->reg_ref[i], g->reg_read[i], &g->reg_cfg, &all[i]);
+    if (rc != VGX_OK) return rc;
+    auto ia = g->index.find(g->reg_ref[i]);
+    auto ib = g->index.find(g->reg_read[i]);
+    if (ia == g->index.end() || ib == g->index.end())
+      VGX_FAIL(c, VGX_ERR_NOT_FOUND, "registration constraint references a submap without a node");
+    all[i].ref_node = ia->second;
+    all[i].read_node = ib->second;
+    if (all[i].n == 0 || all[i].factor == 0.0) g->zero_weight = true;
+    g->residuals_global += all[i].n;
+  }
+  std::vector<int> owner(P, 0);
+  if (c->nranks > 1) {
+    std::vector<int> order(P);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return all[a].n > all[b].n; });
+    std::vector<int64_t> load(c->nranks, 0);
+    for (int i : order) {
+      int best = 0;
+      for (int r = 1; r < c->nranks; ++r)
+        if (load[r] < load[best]) best = r;
+      owner[i] = best;
+      load[best] += all[i].n;
+    }
+  }
+  g->local.clear();
+  std::vector<RegConstraintDev> cons;
+  std::vector<RegTile> tiles;
+  std::vector<int> tile_begin;
+  g->residuals_local = 0;
+  for (int i = 0; i < P; ++i) {
+    if (owner[i] != c->rank) continue;
+    g->local.push_back(i);
+    tile_begin.push_back((int)tiles.size());
+    for (int s = 0; s < all[i].n; s += VGX_REG_TILE_POINTS) {
+      RegTile t;
+      t.constraint = (int)cons.size();
+      t.start = s;
+      t.count = std::min(VGX_REG_TILE_POINTS, all[i].n - s);
+      t.pad = 0;
+      tiles.push_back(t);
+    }
+    cons.push_back(all[i]);
+    g->residuals_local += all[i].n;
+  }
+  tile_begin.push_back((int)tiles.size());
+  g->n_local = (int)cons.size();
+  g->n_tiles = (int)tiles.size();
+  g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
+  g->n_blk = g->n_rel_local + g->n_local;
+
+  // ---- off-diagonal block index over ALL edges (identical on every rank)
+  std::map<std::pair<int, int>, int> block_of;
+  std::vector<int>& block_nodes = g->block_nodes;
+  block_nodes.clear();
+  auto block_id = [&](int a, int b) {
+    std::pair<int, int> key(std::min(a, b), std::max(a, b));
+    auto it = block_of.find(key);
+    if (it != block_of.end()) return it->second;
+    int id = (int)block_of.size();
+    block_of[key] = id;
+    block_nodes.push_back(key.first);
+    block_nodes.push_back(key.second);
+    return id;
+  };
+  for (const auto& e : g->rel) block_id(e.a, e.b);
+  for (int i = 0; i < P; ++i) block_id(all[i].ref_node, all[i].read_node);
+  g->E = (int)block_of.size();
+
+  // ---- CSR of contributions per output block (local blocks only)
+  std::vector<std::vector<int2>> lists(N + g->E);
+  auto add_items = [&](int blk, int a, int b) {
+    lists[a].push_back(make_int2(blk, 0));
+    lists[b].push_back(make_int2(blk, 1));
+    const int ob = N + block_id(a, b);
+    lists[ob].push_back(make_int2(blk, a < b ? 2 : 3));
+  };
+  for (int e = 0; e < g->n_rel_local; ++e) add_items(e, g->rel[e].a, g->rel[e].b);
+  for (int k = 0; k < g->n_local; ++k) add_items(g->n_rel_local + k, cons[k].ref_node, cons[k].read_node);
+  std::vector<int> csr_begin(N + g->E + 1, 0);
+  std::vector<int2> items;
+  for (int ob = 0; ob < N + g->E; ++ob) {
+    csr_begin[ob] = (int)items.size();
+    items.insert(items.end(), lists[ob].begin(), lists[ob].end());
+  }
+  csr_begin[N + g->E] = (int)items.size();
+
+  // ---- reduced offsets
+  std::vector<int> red(N, -1);
+  int n = 0;
+  for (int i = 0; i < N; ++i)
+    if (!g->constant[i]) { red[i] = n; n += 4; }
+  g->n_free = n;
+  g->packed_len = PACK_HDR + 20 * (size_t)N + 16 * (size_t)g->E;
+
+  cudaError_t e = cudaSuccess;
+  cudaStream_t st = c->stream;
+  if (e == cudaSuccess) e = upload_vec(&g->d_cons, cons, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_tiles, tiles, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_tile_begin, tile_begin, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_block_nodes, block_nodes, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_red_offset, red, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_x, g->x, st);
+  auto dmalloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 8));
+  };
+  dmalloc((void**)&g->d_poses, sizeof(RegPoseConst) * g->n_local);
+  dmalloc((void**)&g->d_partials, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_tiles);
+  dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
+  dmalloc((void**)&g->d_blk, sizeof(double) * BLK_STRIDE * (size_t)g->n_blk);
+  dmalloc((void**)&g->d_xc, sizeof(double) * 4 * N);
+  dmalloc((void**)&g->d_packed[0], sizeof(double) * g->packed_len);
+  dmalloc((void**)&g->d_packed[1], sizeof(double) * g->packed_len);
+  dmalloc((void**)&g->d_A, sizeof(double) * (size_t)(n + 1) * (n + 1));
+  dmalloc((void**)&g->d_scale, sizeof(double) * n);
+  dmalloc((void**)&g->d_diag, sizeof(double) * n);
+  dmalloc((void**)&g->d_gs, sizeof(double) * n);
+  dmalloc((void**)&g->d_step, sizeof(double) * n);
+  dmalloc((void**)&g->d_state, sizeof(LmState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&g->h_state, sizeof(LmState));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free_tables(g);
+    c->set_error(std::string("graph table build: ") + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? VGX_ERR_NOMEM : VGX_ERR_CUDA;
+  }
+  g->dirty = false;
+  return VGX_OK;
+}
+
+// ------------------------------------------------------------------ evaluation pipeline
+static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_packed, bool jacobian,
+                        bool exclude_reg) {
+  cudaStream_t st = c->stream;
+  const bool do_reg = !exclude_reg && g->n_local > 0;
+  if (do_reg) {
+    {
+      VgxLaunchScope s(c, 5);
+      vgx_launch_reg_pose_setup(st, g->d_cons, d_x, g->d_poses, g->n_local);
+    }
+    {
+      VgxLaunchScope s(c, 0);
+      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->d_partials, jacobian);
+    }
+    {
+      VgxLaunchScope s(c, 5);
+      vgx_launch_reg_finalize(st, g->d_cons, g->d_tile_begin, g->d_partials, g->d_csum, g->n_local);
+    }
+  }
+  {
+    VgxLaunchScope s(c, 5, (g->n_rel_local > 0) + (g->n_local > 0) + 2);
+    if (g->n_rel_local > 0)
+      rel_blocks_kernel<<<(g->n_rel_local + 63) / 64, 64, 0, st>>>(g->d_rel, d_x, g->d_blk, g->n_rel_local);
+    if (g->n_local > 0)
+      reg_expand_kernel<<<g->n_local, 96, 0, st>>>(g->d_csum, g->d_blk + (size_t)g->n_rel_local * BLK_STRIDE,
+                                                   g->n_local, do_reg ? 0 : 1);
+    const int nob = g->N + g->E;
+    assemble_kernel<<<(nob + 3) / 4, 128, 0, st>>>(g->d_blk, g->d_csr_begin, g->d_csr_items, d_packed,
+                                                   g->N, g->E);
+    cost_kernel<<<1, 256, 0, st>>>(g->d_blk, g->n_blk, d_packed);
+  }
+  VGX_CUDA(c, cudaGetLastError());
+  return vgx_nccl_allreduce_sum_f64(c, d_packed, g->packed_len);
+}
+
+static int prepare(vgx_ctx* c, VgxGraph** out) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  if (g->N == 0) VGX_FAIL(c, VGX_ERR_INVALID, "pose graph has no nodes");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  if (g->dirty) {
+    int rc = build_tables(c, g);
+    if (rc != VGX_OK) return rc;
+  }
+  *out = g;
+  return VGX_OK;
+}
+
+// ------------------------------------------------------------------ C-ABI: b2
+extern "C" int vgx_graph_set_nodes(vgx_ctx* c, int n, const uint32_t* ids, const double* xyzyaw,
+                                   const uint8_t* constant) {
+  if (!c || n < 0 || (n > 0 && (!ids || !xyzyaw))) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  std::map<uint32_t, int> index;
+  for (int i = 0; i < n; ++i) {
+    if (index.count(ids[i])) VGX_FAIL(c, VGX_ERR_INVALID, "duplicate submap id in node list");
+    index[ids[i]] = i;
+  }
+  g->N = n;
+  g->ids.assign(ids, ids + n);
+  g->x.assign(xyzyaw, xyzyaw + 4 * (size_t)n);
+  g->constant.assign(n, 0);
+  if (constant)
+    for (int i = 0; i < n; ++i) g->constant[i] = constant[i] ? 1 : 0;
+  g->index.swap(index);
+  g->rel.clear();
+  g->reg_ref.clear();
+  g->reg_read.clear();
+  g->dirty = true;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_set_poses(vgx_ctx* c, const double* xyzyaw) {
+  if (!c || !xyzyaw) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g || g->N == 0) VGX_FAIL(c, VGX_ERR_INVALID, "pose graph has no nodes");
+  g->x.assign(xyzyaw, xyzyaw + 4 * (size_t)g->N);
+  if (!g->dirty) {
+    VGX_CUDA(c, cudaSetDevice(c->device));
+    // stage through pinned memory so the copy is a true async H2D
+    int rc = c->ensure_pinned(sizeof(double) * 4 * g->N);
+    if (rc != VGX_OK) return rc;
+    VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(c->h_pinned, xyzyaw, sizeof(double) * 4 * g->N);
+    VGX_CUDA(c, cudaMemcpyAsync(g->d_x, c->h_pinned, sizeof(double) * 4 * g->N, cudaMemcpyHostToDevice,
+                                c->stream));
+  }
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_get_poses(vgx_ctx* c, double* xyzyaw) {
+  if (!c || !xyzyaw) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  memcpy(xyzyaw, g->x.data(), sizeof(double) * 4 * g->N);
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_set_relative_edges(vgx_ctx* c, int m, const uint32_t* ids_a,
+                                            const uint32_t* ids_b, const double* t_obs,
+                                            const double* sqrt_info) {
+  if (!c || m < 0 || (m > 0 && (!ids_a || !ids_b || !t_obs || !sqrt_info))) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  std::vector<VgxRelEdge> rel(m);
+  for (int i = 0; i < m; ++i) {
+    auto ia = g->index.find(ids_a[i]);
+    auto ib = g->index.find(ids_b[i]);
+    if (ia == g->index.end() || ib == g->index.end())
+      VGX_FAIL(c, VGX_ERR_NOT_FOUND, "relative-pose edge references a submap without a node");
+    if (ia->second == ib->second) VGX_FAIL(c, VGX_ERR_INVALID, "relative-pose edge from a node to itself");
+    rel[i].a = ia->second;
+    rel[i].b = ib->second;
+    rel[i].t_obs[0] = t_obs[4 * i]; rel[i].t_obs[1] = t_obs[4 * i + 1]; rel[i].t_obs[2] = t_obs[4 * i + 2];
+    rel[i].yaw_obs = t_obs[4 * i + 3];
+    memcpy(rel[i].L, sqrt_info + 16 * (size_t)i, sizeof(double) * 16);
+  }
+  g->rel.swap(rel);
+  g->dirty = true;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_set_registration_constraints(vgx_ctx* c, int p, const uint32_t* ref_ids,
+                                                      const uint32_t* read_ids,
+                                                      const vgx_reg_config* cfg) {
+  if (!c || p < 0 || (p > 0 && (!ref_ids || !read_ids))) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  if (cfg) g->reg_cfg = *cfg;
+  for (int i = 0; i < p; ++i) {
+    if (ref_ids[i] == read_ids[i]) VGX_FAIL(c, VGX_ERR_INVALID, "cannot constrain a submap to itself");
+    if (!g->index.count(ref_ids[i]) || !g->index.count(read_ids[i]))
+      VGX_FAIL(c, VGX_ERR_NOT_FOUND, "graph contains no node for a registration constraint's submap");
+  }
+  g->reg_ref.assign(ref_ids, ref_ids + p);
+  g->reg_read.assign(read_ids, read_ids + p);
+  g->dirty = true;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_num_registration_residuals(vgx_ctx* c, int64_t* local, int64_t* global) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  if (local) *local = g->residuals_local;
+  if (global) *global = g->residuals_global;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_eval_async(vgx_ctx* c, int exclude_registration) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  return eval_enqueue(c, g, g->d_x, g->d_packed[0], true, exclude_registration != 0);
+}
+
+extern "C" int vgx_graph_eval(vgx_ctx* c, int exclude_registration, double* cost, double* gradient,
+                              double* H) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  rc = eval_enqueue(c, g, g->d_x, g->d_packed[0], true, exclude_registration != 0);
+  if (rc != VGX_OK) return rc;
+  rc = c->ensure_pinned(sizeof(double) * g->packed_len);
+  if (rc != VGX_OK) return rc;
+  double* h = (double*)c->h_pinned;
+  VGX_CUDA(c, cudaMemcpyAsync(h, g->d_packed[0], sizeof(double) * g->packed_len, cudaMemcpyDeviceToHost,
+                              c->stream));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int N = g->N, dim = 4 * N;
+  if (cost) *cost = h[0];
+  if (gradient) memcpy(gradient, h + PACK_HDR, sizeof(double) * dim);
+  if (H) {
+    memset(H, 0, sizeof(double) * (size_t)dim * dim);
+    const double* D = h + PACK_HDR + dim;
+    const double* O = D + 16 * (size_t)N;
+    for (int i = 0; i < N; ++i)
+      for (int r = 0; r < 4; ++r)
+        for (int q = 0; q < 4; ++q) H[(size_t)(4 * i + r) * dim + 4 * i + q] = D[16 * (size_t)i + 4 * r + q];
+    const std::vector<int>& bn = g->block_nodes;
+    for (int b = 0; b < g->E; ++b) {
+      const int i = bn[2 * b], j = bn[2 * b + 1];
+      for (int r = 0; r < 4; ++r)
+        for (int q = 0; q < 4; ++q) {
+          const double v = O[16 * (size_t)b + 4 * r + q];
+          H[(size_t)(4 * i + r) * dim + 4 * j + q] = v;
+          H[(size_t)(4 * j + q) * dim + 4 * i + r] = v;
+        }
+    }
+  }
+  if (!exclude_registration && g->zero_weight) return VGX_ZERO_WEIGHT;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_registration_costs(vgx_ctx* c, double* per_constraint) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  if (!per_constraint) return VGX_ERR_INVALID;
+  rc = eval_enqueue(c, g, g->d_x, g->d_packed[1], false, false);
+  if (rc != VGX_OK) return rc;
+  const int P = (int)g->reg_ref.size();
+  std::vector<double> cs((size_t)g->n_local * VGX_REG_NSTRIDE + 1);
+  if (g->n_local > 0)
+    VGX_CUDA(c, cudaMemcpyAsync(cs.data(), g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * g->n_local,
+                                cudaMemcpyDeviceToHost, c->stream));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < P; ++i) per_constraint[i] = 0.0;
+  for (int k = 0; k < g->n_local; ++k) per_constraint[g->local[k]] = cs[(size_t)k * VGX_REG_NSTRIDE + 20];
+  return VGX_OK;
+}
+
+extern "C" void vgx_solver_options_default(vgx_solver_options* o) {
+  if (!o) return;
+  o->max_num_iterations = 50;
+  o->parameter_tolerance = 3e-3;  // pose_graph.cpp:93
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_solver_time_s = 4.0;     // pose_graph.cpp:95
+  o->jacobi_scaling = 1;
+  o->exclude_registration = 0;
+}
+
+static double wall_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, double* xyzyaw_out,
+                               vgx_solver_summary* summary) {
+  const double t0 = wall_s();
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  vgx_solver_options od;
+  vgx_solver_options_default(&od);
+  const vgx_solver_options* o = opts ? opts : &od;
+  const bool excl = o->exclude_registration != 0;
+  vgx_solver_summary S;
+  memset(&S, 0, sizeof(S));
+  const int N = g->N, n = g->n_free;
+  cudaStream_t st = c->stream;
+  if (!excl && g->zero_weight) {
+    S.termination = 6;
+    if (summary) *summary = S;
+    VGX_FAIL(c, VGX_ZERO_WEIGHT, "a registration constraint has zero summed weight (Evaluate == false)");
+  }
+  const size_t chol_smem = sizeof(double) * ((size_t)CH_NB * 33 + (size_t)std::max(n + 1 - CH_NB, 1) * 33);
+  if (chol_smem > 227 * 1024)
+    VGX_FAIL(c, VGX_ERR_CAPACITY, "pose graph too large for the single-CTA dense solver (max ~219 free nodes)");
+  VGX_CUDA(c, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+
+  LmOpts lo;
+  lo.max_num_iterations = o->max_num_iterations;
+  lo.parameter_tolerance = o->parameter_tolerance;
+  lo.function_tolerance = o->function_tolerance;
+  lo.gradient_tolerance = o->gradient_tolerance;
+  lo.max_radius = o->max_trust_region_radius;
+  lo.min_radius = o->min_trust_region_radius;
+  lo.min_relative_decrease = o->min_relative_decrease;
+  lo.min_lm_diagonal = o->min_lm_diagonal;
+  lo.max_lm_diagonal = o->max_lm_diagonal;
+  lo.jacobi_scaling = o->jacobi_scaling;
+
+  int cur = 0;
+  rc = eval_enqueue(c, g, g->d_x, g->d_packed[cur], true, excl);
+  if (rc != VGX_OK) return rc;
+  {
+    VgxLaunchScope s(c, 4);
+    lm_init_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_red_offset, N, g->d_state,
+                                      o->initial_trust_region_radius, lo);
+  }
+  VGX_CUDA(c, cudaMemcpyAsync(g->h_state, g->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+  VGX_CUDA(c, cudaStreamSynchronize(st));
+  S.initial_cost = g->h_state->cost;
+  bool timed_out = false;
+  while (!g->h_state->done && n > 0) {
+    // (single-rank only: ranks must take identical decisions or the all-reduce would hang)
+    if (c->nranks == 1 && wall_s() - t0 >= o->max_solver_time_s) { timed_out = true; break; }
+    {
+      VgxLaunchScope s(c, 4, 4);
+      VGX_CUDA(c, cudaMemsetAsync(g->d_A, 0, sizeof(double) * (size_t)(n + 1) * (n + 1), st));
+      const int nthreads = std::max(16 * (N + g->E), 4 * N);
+      lm_build_kernel<<<std::min(296, (nthreads + 255) / 256), 256, 0, st>>>(
+          g->d_packed[cur], g->d_red_offset, g->d_block_nodes, N, g->E, n, g->d_A, g->d_scale, g->d_diag,
+          g->d_gs, g->d_state, lo);
+      lm_persist_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_red_offset, N, g->d_scale, g->d_diag,
+                                           g->d_state, lo);
+      chol_kernel<<<1, 1024, chol_smem, st>>>(g->d_A, n, g->d_state);
+      lm_step_kernel<<<1, 1024, sizeof(double) * n, st>>>(g->d_A, n, N, g->d_red_offset, g->d_scale,
+                                                         g->d_diag, g->d_gs, g->d_x, g->d_xc, g->d_step,
+                                                         g->d_state);
+    }
+    VGX_CUDA(c, cudaGetLastError());
+    // candidate evaluated with Jacobians so an accepted step needs no second pass
+    rc = eval_enqueue(c, g, g->d_xc, g->d_packed[1 - cur], true, excl);
+    if (rc != VGX_OK) return rc;
+    {
+      VgxLaunchScope s(c, 4);
+      lm_decide_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_packed[1 - cur], g->d_red_offset, N,
+                                          g->d_x, g->d_xc, g->d_state, lo, 1);
+    }
+    VGX_CUDA(c, cudaMemcpyAsync(g->h_state, g->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+    VGX_CUDA(c, cudaStreamSynchronize(st));
+    if (g->h_state->accepted) cur = 1 - cur;
+  }
+  if (n == 0) { g->h_state->termination = 2; }
+  // keep the packed result of the current poses in slot 0 for later vgx_graph_eval users
+  VGX_CUDA(c, cudaMemcpyAsync(g->x.data(), g->d_x, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, st));
+  VGX_CUDA(c, cudaStreamSynchronize(st));
+  S.iterations = g->h_state->iterations;
+  S.num_successful_steps = g->h_state->successful;
+  S.num_residual_evals = g->h_state->evals;
+  S.termination = timed_out ? 4 : g->h_state->termination;
+  S.final_cost = g->h_state->cost;
+  S.total_time_s = wall_s() - t0;
+  if (xyzyaw_out) memcpy(xyzyaw_out, g->x.data(), sizeof(double) * 4 * N);
+  if (summary) *summary = S;
+  if (S.termination == 6) VGX_FAIL(c, VGX_ERR_INVALID, "solver failure: too many consecutive invalid steps");
+  return VGX_OK;
+}

@@ -1,0 +1,275 @@
+// Device-side restatement of RegistrationCostFunction::Evaluate
+// (voxgraph/src/backend/constraint/cost_functions/registration_cost_function.cpp:58-298)
+// and voxblox Interpolator::getVoxelsAndQVector.
+//
+// This translation unit family is compiled with -fmad=false: every float expression of
+// the reference is evaluated operation by operation (IEEE RN, no contraction) so that
+// voxel/block indices are bit-exact and residuals/Jacobians match the reference's float
+// path.  FMAs are used explicitly (fma()) only where the product is exact in double.
+#pragma once
+
+#include <math.h>
+
+#include "vgx_internal.h"
+
+#define VGX_COORD_EPS 1e-6f
+
+// Per-constraint, per-evaluation pose block (cpp:61-110).
+struct RegPoseConst {
+  float qw, qz;                          // T_reading__reference rotation (yaw-only quaternion)
+  float tx, ty, tz;                      // T_reading__reference translation
+  float cos_e, sin_e, cos_emo, sin_emo;  // cpp:91-96
+  float dxs, dyc, dxc, dys;              // (xe-xo)*sin_e, (ye-yo)*cos_e, (xe-xo)*cos_e, (ye-yo)*sin_e
+};
+
+// Reading-submap view + reference points of one residual block.
+struct RegConstraintDev {
+  const float *px, *py, *pz, *pd, *pw;  // reference registration points (SoA)
+  int n;
+  int ref_node, read_node;
+  VgxHash hash;        // reading submap block hash
+  const float* view;   // reading bricks: distance, NaN where unobserved
+  float voxel_size, voxel_size_inv, block_size, block_size_inv;
+  int vps, vps_shift;
+  double factor;       // num_residuals / summed_reference_weight (cpp:274)
+  double no_corr;      // config.no_correspondence_cost
+};
+
+struct TrigHostLibm {  // host: the reference's own calls, std::cos(float) -> cosf
+  static __host__ __device__ float cosf_(float x) {
+#ifdef __CUDA_ARCH__
+    return (float)cos((double)x);
+#else
+    return ::cosf(x);
+#endif
+  }
+  static __host__ __device__ float sinf_(float x) {
+#ifdef __CUDA_ARCH__
+    return (float)sin((double)x);
+#else
+    return ::sinf(x);
+#endif
+  }
+};
+struct TrigDevice {  // double evaluation rounded once to float
+  static __host__ __device__ float cosf_(float x) { return (float)cos((double)x); }
+  static __host__ __device__ float sinf_(float x) { return (float)sin((double)x); }
+};
+
+// Eigen Quaternion::_transformVector specialised to q = (w, 0, 0, z) (minkindr rotate()).
+__host__ __device__ __forceinline__ void vgx_rotate_yaw(float w, float z, float v0, float v1,
+                                                        float v2, float& o0, float& o1, float& o2) {
+  float uv0 = -(z * v1);
+  float uv1 = z * v0;
+  uv0 += uv0;
+  uv1 += uv1;
+  const float c0 = -(z * uv1);
+  const float c1 = z * uv0;
+  o0 = (v0 + w * uv0) + c0;
+  o1 = (v1 + w * uv1) + c1;
+  o2 = v2;
+}
+
+// minkindr RotationQuaternion::exp for a pure-yaw rotation vector (Appendix A.1).
+__host__ __device__ __forceinline__ void vgx_yaw_quat(float yaw, float& qw, float& qz) {
+  const float sq = yaw * yaw;
+  const double theta = (double)sqrtf(sq);
+  double na;
+  if (theta < 1.220703125e-4) {  // eps^(1/4) for double
+    na = 0.5 + (theta * theta) * (1.0 / 48.0);
+  } else {
+    na = sin(theta * 0.5) / theta;
+  }
+  qw = (float)cos(theta * 0.5);
+  qz = (float)((double)yaw * na);
+}
+
+template <class Trig>
+__host__ __device__ inline void vgx_reg_pose_setup(const double* ref, const double* read,
+                                                   RegPoseConst& P) {
+  const float xo = (float)ref[0], yo = (float)ref[1], zo = (float)ref[2], tho = (float)ref[3];
+  const float xe = (float)read[0], ye = (float)read[1], ze = (float)read[2], the = (float)read[3];
+  float wo, qo, we, qe;
+  vgx_yaw_quat(tho, wo, qo);
+  vgx_yaw_quat(the, we, qe);
+  P.cos_e = Trig::cosf_(the);
+  P.sin_e = Trig::sinf_(the);
+  P.cos_emo = Trig::cosf_(the - tho);
+  P.sin_emo = Trig::sinf_(the - tho);
+  P.dxs = (xe - xo) * P.sin_e;
+  P.dyc = (ye - yo) * P.cos_e;
+  P.dxc = (xe - xo) * P.cos_e;
+  P.dys = (ye - yo) * P.sin_e;
+  // T_mission__reading.inverse(): q^-1 = (we, -qe), t = -(q^-1 rotate t_read)
+  const float iw = we, iz = -qe;
+  float r0, r1, r2;
+  vgx_rotate_yaw(iw, iz, xe, ye, ze, r0, r1, r2);
+  const float ti0 = -r0, ti1 = -r1, ti2 = -r2;
+  // inverse * T_mission__reference
+  P.qw = iw * wo - iz * qo;
+  P.qz = iw * qo + iz * wo;
+  vgx_rotate_yaw(iw, iz, xo, yo, zo, r0, r1, r2);
+  P.tx = ti0 + r0;
+  P.ty = ti1 + r1;
+  P.tz = ti2 + r2;
+}
+
+#ifdef __CUDACC__
+// Result of evaluating one registration point.
+struct RegPointResult {
+  double r;        // unnormalised residual (cpp:161-166)
+  float jr[4];     // unnormalised dResidual/dReferencePose (cpp:234-235)
+  float je3;       // dResidual/dReadingYaw; je[0..2] == -jr[0..2] exactly
+  bool ok;         // interpolation possible
+};
+
+__device__ __forceinline__ int vgx_floor_idx(float v) { return (int)floorf(v); }
+
+// getVoxelsAndQVector: returns false when a block is missing or a corner unobserved.
+__device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, float p0, float p1,
+                                                  float p2, float d[8], float& ox, float& oy,
+                                                  float& oz) {
+  const int vps = C.vps;
+  int b0 = vgx_floor_idx(p0 * C.block_size_inv + VGX_COORD_EPS);
+  int b1 = vgx_floor_idx(p1 * C.block_size_inv + VGX_COORD_EPS);
+  int b2 = vgx_floor_idx(p2 * C.block_size_inv + VGX_COORD_EPS);
+  int slot = vgx_hash_find(C.hash, b0, b1, b2);
+  if (slot < 0) return false;
+  const float or0 = (float)b0 * C.block_size, or1 = (float)b1 * C.block_size,
+              or2 = (float)b2 * C.block_size;
+  int v0 = vgx_floor_idx((p0 - or0) * C.voxel_size_inv + VGX_COORD_EPS);
+  int v1 = vgx_floor_idx((p1 - or1) * C.voxel_size_inv + VGX_COORD_EPS);
+  int v2 = vgx_floor_idx((p2 - or2) * C.voxel_size_inv + VGX_COORD_EPS);
+  v0 = max(min(v0, vps - 1), 0);
+  v1 = max(min(v1, vps - 1), 0);
+  v2 = max(min(v2, vps - 1), 0);
+  bool moved = false;
+  if (p0 - (or0 + ((float)v0 + 0.5f) * C.voxel_size) < 0) {
+    if (--v0 < 0) { --b0; v0 += vps; moved = true; }
+  }
+  if (p1 - (or1 + ((float)v1 + 0.5f) * C.voxel_size) < 0) {
+    if (--v1 < 0) { --b1; v1 += vps; moved = true; }
+  }
+  if (p2 - (or2 + ((float)v2 + 0.5f) * C.voxel_size) < 0) {
+    if (--v2 < 0) { --b2; v2 += vps; moved = true; }
+  }
+  if (moved) {
+    slot = vgx_hash_find(C.hash, b0, b1, b2);
+    if (slot < 0) return false;
+  }
+  // q vector offsets from the base corner (block origin recomputed from the moved index)
+  ox = (p0 - ((float)b0 * C.block_size + ((float)v0 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+  oy = (p1 - ((float)b1 * C.block_size + ((float)v1 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+  oz = (p2 - ((float)b2 * C.block_size + ((float)v2 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+
+  const bool c0 = (v0 == vps - 1), c1 = (v1 == vps - 1), c2 = (v2 == vps - 1);
+  const int sh = C.vps_shift;
+  const size_t vpb = (size_t)1 << (3 * sh);
+  const int x0 = v0, x1 = (v0 + 1) & (vps - 1);
+  const int yy0 = v1 << sh, yy1 = ((v1 + 1) & (vps - 1)) << sh;
+  const int zz0 = v2 << (2 * sh), zz1 = ((v2 + 1) & (vps - 1)) << (2 * sh);
+  if (!(c0 | c1 | c2)) {
+    const float* base = C.view + (size_t)slot * vpb;
+    // corner i: x = bit2, y = bit1, z = bit0
+    d[0] = __ldg(base + x0 + yy0 + zz0);
+    d[1] = __ldg(base + x0 + yy0 + zz1);
+    d[2] = __ldg(base + x0 + yy1 + zz0);
+    d[3] = __ldg(base + x0 + yy1 + zz1);
+    d[4] = __ldg(base + x1 + yy0 + zz0);
+    d[5] = __ldg(base + x1 + yy0 + zz1);
+    d[6] = __ldg(base + x1 + yy1 + zz0);
+    d[7] = __ldg(base + x1 + yy1 + zz1);
+  } else {
+    int s[8];
+    s[0] = slot;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const bool ux = (i & 4) && c0, uy = (i & 2) && c1, uz = (i & 1) && c2;
+      // a corner that stays inside the base block in every crossing axis reuses an earlier slot
+      const int j = (ux ? 4 : 0) | (uy ? 2 : 0) | (uz ? 1 : 0);
+      if (j == i) {
+        s[i] = vgx_hash_find(C.hash, b0 + (ux ? 1 : 0), b1 + (uy ? 1 : 0), b2 + (uz ? 1 : 0));
+        if (s[i] < 0) return false;
+      } else {
+        s[i] = s[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int lin = ((i & 4) ? x1 : x0) + ((i & 2) ? yy1 : yy0) + ((i & 1) ? zz1 : zz0);
+      d[i] = __ldg(C.view + (size_t)s[i] * vpb + lin);
+    }
+  }
+  // isObservedVoxel failed <=> NaN in the view
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ok = ok && (d[i] == d[i]);
+  return ok;
+}
+
+template <bool kJacobian>
+__device__ __forceinline__ RegPointResult vgx_reg_point(const RegConstraintDev& C,
+                                                        const RegPoseConst& P, float xi, float yi,
+                                                        float zi, float dist, float w) {
+  RegPointResult R;
+  // cpp:128-129  reading_coordinate = T_reading__reference * reference_coordinate
+  float r0, r1, r2;
+  vgx_rotate_yaw(P.qw, P.qz, xi, yi, zi, r0, r1, r2);
+  const float p0 = r0 + P.tx, p1 = r1 + P.ty, p2 = r2 + P.tz;
+  float d[8], ox = 0, oy = 0, oz = 0;
+  R.ok = vgx_interp_gather(C, p0, p1, p2, d, ox, oy, oz);
+  R.jr[0] = R.jr[1] = R.jr[2] = R.jr[3] = 0.f;
+  R.je3 = 0.f;
+  if (!R.ok) {
+    R.r = (double)w * C.no_corr;  // cpp:164-166
+    return R;
+  }
+  // a = B1 * distances^T (registration_cost_function.h:73-81)
+  float a[8];
+  a[0] = d[0];
+  a[1] = -d[0] + d[4];
+  a[2] = -d[0] + d[2];
+  a[3] = -d[0] + d[1];
+  a[4] = d[0] - d[2] - d[4] + d[6];
+  a[5] = d[0] - d[1] - d[2] + d[3];
+  a[6] = d[0] - d[1] - d[4] + d[5];
+  a[7] = -d[0] + d[1] + d[2] - d[3] + d[4] - d[5] - d[6] + d[7];
+  float q[8];
+  q[0] = 1.0f; q[1] = ox; q[2] = oy; q[3] = oz;
+  q[4] = ox * oy; q[5] = oy * oz; q[6] = oz * ox; q[7] = ox * oy * oz;
+  float interp = q[0] * a[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) interp = interp + q[k] * a[k];
+  R.r = ((double)dist - (double)interp) * (double)w;  // cpp:158-163
+  if (kJacobian) {
+    // cpp:183-202: double deltas, float entries
+    const double inv = (double)C.voxel_size_inv;
+    const double Dx = (double)q[1], Dy = (double)q[2], Dz = (double)q[3];
+    const float finv = (float)inv;
+    const float iDx = (float)(inv * Dx), iDy = (float)(inv * Dy), iDz = (float)(inv * Dz);
+    const float iDyDz = (float)(inv * Dy * Dz), iDxDz = (float)(inv * Dx * Dz),
+                iDxDy = (float)(inv * Dx * Dy);
+    // cpp:204-205: pInterp_pr = a * pQ_pr summed k = 0..7; the structurally zero entries of
+    // pQ_pr add (+-0) and are skipped (value-identical)
+    float g0 = a[1] * finv;
+    g0 = g0 + a[4] * iDy; g0 = g0 + a[6] * iDz; g0 = g0 + a[7] * iDyDz;
+    float g1 = a[2] * finv;
+    g1 = g1 + a[4] * iDx; g1 = g1 + a[5] * iDz; g1 = g1 + a[7] * iDxDz;
+    float g2 = a[3] * finv;
+    g2 = g2 + a[5] * iDy; g2 = g2 + a[6] * iDx; g2 = g2 + a[7] * iDxDy;
+    // cpp:214-227
+    const float ar03 = xi * P.sin_emo - yi * P.cos_emo;
+    const float ar13 = xi * P.cos_emo + yi * P.sin_emo;
+    const float ae03 = -xi * P.sin_emo + yi * P.cos_emo + P.dxs - P.dyc;
+    const float ae13 = -xi * P.cos_emo - yi * P.sin_emo + P.dxc + P.dys;
+    // cpp:234-239: (-w * pInterp_pr) * A, row sums (k0 + k1) + k2
+    const float m0 = -w * g0, m1 = -w * g1, m2 = -w * g2;
+    R.jr[0] = m0 * P.cos_e + m1 * (-P.sin_e);
+    R.jr[1] = m0 * P.sin_e + m1 * P.cos_e;
+    R.jr[2] = m2;
+    R.jr[3] = m0 * ar03 + m1 * ar13;
+    R.je3 = m0 * ae03 + m1 * ae13;
+  }
+  return R;
+}
+#endif  // __CUDACC__

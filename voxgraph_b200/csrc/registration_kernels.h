@@ -1,0 +1,28 @@
+// Host-visible declarations of the registration kernels (registration.cu).
+#pragma once
+
+#include "vgx_internal.h"
+
+struct RegConstraintDev;
+struct RegPoseConst;
+
+#define VGX_REG_THREADS 256
+#define VGX_REG_TILE_POINTS 2048   // points per CTA (8 per thread)
+#define VGX_REG_NSUM 21            // 15 (upper 5x5) + 5 (gradient) + 1 (cost)
+#define VGX_REG_NSTRIDE 24
+
+struct RegTile {
+  int constraint;
+  int start;
+  int count;
+  int pad;
+};
+
+void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
+                               RegPoseConst* poses, int n);
+void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
+                           const RegTile* tiles, int n_tiles, double* partials, bool jacobian);
+void vgx_launch_reg_finalize(cudaStream_t st, const RegConstraintDev* cons, const int* tile_begin,
+                             const double* partials, double* csum, int n);
+int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
+                        RegConstraintDev* out);

@@ -1,0 +1,383 @@
+// Context + brick store: voxblox::Layer/Block/AnyIndexHash replacement in HBM.
+// Reference semantics: SURVEY.md Appendix A.2 (voxblox core) as used by
+// voxgraph/src/frontend/submap_collection/voxgraph_submap.cpp.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "vgx_internal.h"
+
+// ------------------------------------------------------------------ context
+int vgx_ctx::ensure_scratch(size_t bytes) {
+  if (bytes <= scratch_bytes) return VGX_OK;
+  if (d_scratch) cudaFree(d_scratch);
+  d_scratch = nullptr;
+  scratch_bytes = 0;
+  size_t want = bytes + bytes / 4;
+  VGX_CUDA(this, cudaMalloc(&d_scratch, want));
+  scratch_bytes = want;
+  return VGX_OK;
+}
+
+int vgx_ctx::ensure_pinned(size_t bytes) {
+  if (bytes <= pinned_bytes) return VGX_OK;
+  if (h_pinned) cudaFreeHost(h_pinned);
+  h_pinned = nullptr;
+  pinned_bytes = 0;
+  size_t want = bytes + bytes / 4;
+  VGX_CUDA(this, cudaMallocHost(&h_pinned, want));
+  pinned_bytes = want;
+  return VGX_OK;
+}
+
+extern "C" int vgx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int vgx_ctx_create(int device, vgx_ctx** out) {
+  if (!out) return VGX_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+    return VGX_ERR_CUDA;  // no CPU fallback: the product path needs a GPU
+  if (cudaSetDevice(device) != cudaSuccess) return VGX_ERR_CUDA;
+  vgx_ctx* c = new (std::nothrow) vgx_ctx();
+  if (!c) return VGX_ERR_NOMEM;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return VGX_ERR_CUDA;
+  }
+  *out = c;
+  return VGX_OK;
+}
+
+static void free_points(VgxPoints& p) {
+  if (p.x) cudaFree(p.x);  // one allocation holds all five arrays
+  p = VgxPoints();
+}
+
+static void free_submap(VgxSubmap* s) {
+  if (!s) return;
+  cudaFree(s->hash.keys);
+  cudaFree(s->hash.vals);
+  cudaFree(s->d_block_idx);
+  cudaFree(s->d_dw);
+  cudaFree(s->d_view);
+  cudaFree(s->d_counters);
+  free_points(s->points[0]);
+  free_points(s->points[1]);
+  delete s;
+}
+
+extern "C" void vgx_ctx_destroy(vgx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  vgx_comm_destroy(c);
+  vgx_graph_free(c);
+  for (auto& kv : c->submaps) free_submap(kv.second);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* vgx_last_error(const vgx_ctx* c) { return c ? c->error.c_str() : "null context"; }
+extern "C" void* vgx_ctx_stream(vgx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int vgx_ctx_synchronize(vgx_ctx* c) {
+  if (!c) return VGX_ERR_INVALID;
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VGX_OK;
+}
+
+extern "C" int vgx_profile_enable(vgx_ctx* c, int on) {
+  if (!c) return VGX_ERR_INVALID;
+  c->profile = on != 0;
+  return VGX_OK;
+}
+extern "C" int vgx_profile_reset(vgx_ctx* c) {
+  if (!c) return VGX_ERR_INVALID;
+  for (auto& p : c->prof) p = VgxProfileSlot();
+  c->launches = 0;
+  return VGX_OK;
+}
+extern "C" int vgx_profile_get(vgx_ctx* c, int which, double* total_ms, int64_t* launches) {
+  if (!c || which < 0 || which >= 6) return VGX_ERR_INVALID;
+  if (total_ms) *total_ms = c->prof[which].total_ms;
+  if (launches) *launches = c->prof[which].launches;
+  return VGX_OK;
+}
+extern "C" int64_t vgx_launch_count(vgx_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------ kernels
+__global__ void hash_clear_kernel(uint64_t* keys, int32_t* vals, uint32_t size) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < size) {
+    keys[i] = VGX_EMPTY_KEY;
+    vals[i] = -1;
+  }
+}
+
+// Insert n known-distinct blocks (slot = position in the list).
+__global__ void hash_insert_kernel(VgxHash h, const int32_t* block_idx, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int bx = block_idx[3 * s], by = block_idx[3 * s + 1], bz = block_idx[3 * s + 2];
+  const uint64_t key = vgx_pack_key(bx, by, bz);
+  uint32_t i = vgx_hash_index(bx, by, bz, h.mask);
+  for (;;) {
+    unsigned long long prev =
+        atomicCAS((unsigned long long*)(h.keys + i), (unsigned long long)VGX_EMPTY_KEY,
+                  (unsigned long long)key);
+    if (prev == VGX_EMPTY_KEY || prev == key) {
+      h.vals[i] = s;  // duplicates in the input: last writer wins
+      return;
+    }
+    i = (i + 1) & h.mask;
+  }
+}
+
+// (distance[], weight[]) -> interleaved float2 bricks + registration view.
+__global__ void interleave_kernel(const float* __restrict__ d, const float* __restrict__ w,
+                                  float2* __restrict__ dw, float* __restrict__ view, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dd = d[i], ww = w[i];
+  dw[i] = make_float2(dd, ww);
+  // utils::isObservedVoxel: weight > 1e-6
+  view[i] = (ww > 1e-6f) ? dd : __int_as_float(0x7fc00000);
+}
+
+__global__ void build_view_kernel(const float2* __restrict__ dw, float* __restrict__ view, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 v = dw[i];
+  view[i] = (v.y > 1e-6f) ? v.x : __int_as_float(0x7fc00000);
+}
+
+__global__ void deinterleave_kernel(const float2* __restrict__ dw, float* __restrict__ d,
+                                    float* __restrict__ w, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 v = dw[i];
+  d[i] = v.x;
+  w[i] = v.y;
+}
+
+// ------------------------------------------------------------------ submap management
+static uint32_t table_size_for(int cap) {
+  uint32_t t = 64;
+  while (t < (uint32_t)cap * 2u) t <<= 1;
+  return t;
+}
+
+static int alloc_submap(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int cap, bool with_view,
+                        VgxSubmap** out) {
+  if (!(voxel_size > 0) || vps < 2 || vps > 32 || (vps & (vps - 1)) != 0 || cap < 0)
+    VGX_FAIL(c, VGX_ERR_INVALID, "invalid voxel_size / voxels_per_side / capacity");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  VgxSubmap* old = c->find(id);
+  if (old) {
+    VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_submap(old);
+    c->submaps.erase(id);
+    vgx_graph_invalidate_registration(c);
+  }
+  VgxSubmap* s = new (std::nothrow) VgxSubmap();
+  if (!s) return VGX_ERR_NOMEM;
+  s->id = id;
+  s->voxel_size = voxel_size;
+  // voxblox Layer ctor: inverses by double division, stored as float
+  s->voxel_size_inv = (float)(1.0 / (double)voxel_size);
+  s->block_size = voxel_size * (float)vps;
+  s->block_size_inv = (float)(1.0 / (double)s->block_size);
+  s->vps = vps;
+  s->vox_per_block = vps * vps * vps;
+  s->cap_blocks = cap > 0 ? cap : 1;
+  const uint32_t tsize = table_size_for(s->cap_blocks);
+  s->hash.mask = tsize - 1;
+  const size_t nvox = (size_t)s->cap_blocks * s->vox_per_block;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&s->hash.keys, sizeof(uint64_t) * tsize);
+  if (e == cudaSuccess) e = cudaMalloc(&s->hash.vals, sizeof(int32_t) * tsize);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_block_idx, sizeof(int32_t) * 3 * s->cap_blocks);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_dw, sizeof(float2) * nvox);
+  if (e == cudaSuccess && with_view) e = cudaMalloc(&s->d_view, sizeof(float) * nvox);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, sizeof(int) * 4);
+  if (e != cudaSuccess) {
+    free_submap(s);
+    c->set_error(std::string("submap allocation: ") + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? VGX_ERR_NOMEM : VGX_ERR_CUDA;
+  }
+  hash_clear_kernel<<<(tsize + 255) / 256, 256, 0, c->stream>>>(s->hash.keys, s->hash.vals, tsize);
+  c->launches++;
+  VGX_CUDA(c, cudaMemsetAsync(s->d_counters, 0, sizeof(int) * 4, c->stream));
+  c->submaps[id] = s;
+  *out = s;
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_upload(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int n_blocks,
+                                 const int32_t* block_idx, const float* distance,
+                                 const float* weight) {
+  if (!c) return VGX_ERR_INVALID;
+  if (n_blocks < 0 || (n_blocks > 0 && (!block_idx || !distance || !weight)))
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_upload: null input");
+  VgxSubmap* s = nullptr;
+  int rc = alloc_submap(c, id, voxel_size, vps, n_blocks, true, &s);
+  if (rc != VGX_OK) return rc;
+  s->n_blocks = n_blocks;
+  s->finished = true;
+  if (n_blocks == 0) return VGX_OK;
+  const size_t nvox = (size_t)n_blocks * s->vox_per_block;
+  rc = c->ensure_scratch(2 * nvox * sizeof(float));
+  if (rc != VGX_OK) return rc;
+  float* tmp_d = (float*)c->d_scratch;
+  float* tmp_w = tmp_d + nvox;
+  VGX_CUDA(c, cudaMemcpyAsync(tmp_d, distance, nvox * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VGX_CUDA(c, cudaMemcpyAsync(tmp_w, weight, nvox * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_block_idx, block_idx, sizeof(int32_t) * 3 * n_blocks,
+                              cudaMemcpyHostToDevice, c->stream));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_counters, &s->n_blocks, sizeof(int), cudaMemcpyHostToDevice,
+                              c->stream));
+  hash_insert_kernel<<<(n_blocks + 127) / 128, 128, 0, c->stream>>>(s->hash, s->d_block_idx, n_blocks);
+  interleave_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(tmp_d, tmp_w, s->d_dw,
+                                                                             s->d_view, nvox);
+  c->launches += 2;
+  VGX_CUDA(c, cudaGetLastError());
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // host buffers are the caller's
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_create(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int capacity) {
+  if (!c) return VGX_ERR_INVALID;
+  if (capacity <= 0) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_create: capacity must be > 0");
+  VgxSubmap* s = nullptr;
+  int rc = alloc_submap(c, id, voxel_size, vps, capacity, false, &s);
+  if (rc != VGX_OK) return rc;
+  // new voxblox blocks are zero-initialised (distance 0, weight 0)
+  VGX_CUDA(c, cudaMemsetAsync(s->d_dw, 0, sizeof(float2) * (size_t)capacity * s->vox_per_block,
+                              c->stream));
+  s->finished = false;
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_finish(vgx_ctx* c, uint32_t id) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_finish: unknown submap");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  const size_t nvox = (size_t)s->cap_blocks * s->vox_per_block;
+  if (!s->d_view) VGX_CUDA(c, cudaMalloc(&s->d_view, sizeof(float) * nvox));
+  const size_t used = (size_t)s->n_blocks * s->vox_per_block;
+  if (used > 0) {
+    build_view_kernel<<<(unsigned)((used + 255) / 256), 256, 0, c->stream>>>(s->d_dw, s->d_view, used);
+    c->launches++;
+    VGX_CUDA(c, cudaGetLastError());
+  }
+  s->finished = true;
+  vgx_graph_invalidate_registration(c);
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_free(vgx_ctx* c, uint32_t id) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_free: unknown submap");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_submap(s);
+  c->submaps.erase(id);
+  vgx_graph_invalidate_registration(c);
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_block_count(vgx_ctx* c, uint32_t id, int* n) {
+  if (!c || !n) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_block_count: unknown submap");
+  *n = s->n_blocks;
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_download(vgx_ctx* c, uint32_t id, int max_blocks, int32_t* block_idx,
+                                   float* distance, float* weight, int* n_out) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_download: unknown submap");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  const int n = s->n_blocks;
+  if (n_out) *n_out = n;
+  if (n > max_blocks) VGX_FAIL(c, VGX_ERR_CAPACITY, "vgx_submap_download: max_blocks too small");
+  if (n == 0) return VGX_OK;
+  const size_t nvox = (size_t)n * s->vox_per_block;
+  if (block_idx)
+    VGX_CUDA(c, cudaMemcpyAsync(block_idx, s->d_block_idx, sizeof(int32_t) * 3 * n,
+                                cudaMemcpyDeviceToHost, c->stream));
+  if (distance || weight) {
+    int rc = c->ensure_scratch(2 * nvox * sizeof(float));
+    if (rc != VGX_OK) return rc;
+    float* tmp_d = (float*)c->d_scratch;
+    float* tmp_w = tmp_d + nvox;
+    deinterleave_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(s->d_dw, tmp_d, tmp_w, nvox);
+    c->launches++;
+    VGX_CUDA(c, cudaGetLastError());
+    if (distance)
+      VGX_CUDA(c, cudaMemcpyAsync(distance, tmp_d, nvox * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (weight)
+      VGX_CUDA(c, cudaMemcpyAsync(weight, tmp_w, nvox * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_upload_points(vgx_ctx* c, uint32_t id, int type, int n, const float* xyz,
+                                        const float* distance, const float* weight) {
+  if (!c) return VGX_ERR_INVALID;
+  if (type < 0 || type > 1 || n < 0 || (n > 0 && (!xyz || !distance || !weight)))
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_upload_points: invalid argument");
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_upload_points: unknown submap");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  VgxPoints& p = s->points[type];
+  free_points(p);
+  vgx_graph_invalidate_registration(c);
+  if (n == 0) return VGX_OK;
+  // SoA staging on the host (pinned), one device allocation for the five arrays
+  const size_t stride = ((size_t)n + 31) & ~(size_t)31;
+  int rc = c->ensure_pinned(5 * stride * sizeof(float));
+  if (rc != VGX_OK) return rc;
+  float* h = (float*)c->h_pinned;
+  double sum_w = 0;
+  for (int i = 0; i < n; ++i) {
+    h[i] = xyz[3 * (size_t)i];
+    h[stride + i] = xyz[3 * (size_t)i + 1];
+    h[2 * stride + i] = xyz[3 * (size_t)i + 2];
+    h[3 * stride + i] = distance[i];
+    h[4 * stride + i] = weight[i];
+    sum_w += (double)weight[i];  // cpp:124, in point order
+  }
+  for (size_t i = n; i < stride; ++i)
+    for (int k = 0; k < 5; ++k) h[k * stride + i] = 0.f;
+  float* d = nullptr;
+  VGX_CUDA(c, cudaMalloc(&d, 5 * stride * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d, h, 5 * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    c->set_error(std::string("points upload: ") + cudaGetErrorString(e));
+    return VGX_ERR_CUDA;
+  }
+  p.n = n;
+  p.x = d; p.y = d + stride; p.z = d + 2 * stride; p.dist = d + 3 * stride; p.w = d + 4 * stride;
+  p.sum_w = sum_w;
+  return VGX_OK;
+}

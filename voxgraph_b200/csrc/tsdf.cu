@@ -1,0 +1,391 @@
+// TSDF ray-cast integration into the HBM brick store (boundary b3).
+// Restates voxblox TsdfIntegratorBase::{isPointValid, getVoxelWeight, computeDistance,
+// updateTsdfVoxel}, RayCaster and the Simple/Fast scheduling as
+// driven by PointcloudIntegrator::integratePointcloud
+// (voxgraph/src/frontend/measurement_processors/pointcloud_integrator.cpp:66-84).
+// Compiled with -fmad=false (the float expressions are restated operation by operation).
+//
+// Two passes per scan, one thread per ray, both walking the identical DDA:
+//   1. allocate: insert every block a ray touches into the block hash (atomicCAS on the
+//      key, slot from an atomic counter) - replaces allocateStorageAndGetVoxelPtr +
+//      updateLayerWithStoredBlocks;
+//   2. integrate: per visited voxel a lock-free 64-bit CAS read-modify-write of the
+//      interleaved (distance, weight) pair - replaces the per-voxel mutex.
+// The order in which rays hit a voxel is unspecified (as in the multi-threaded reference).
+#include <math.h>
+#include <string.h>
+
+#include "vgx_internal.h"
+
+#define VGX_EPS 1e-6f
+
+struct TsdfParams {
+  float q[4], t[3];  // T_G_C
+  float voxel_size, voxel_size_inv;
+  int vps, vps_shift;
+  vgx_tsdf_config cfg;
+  int n;
+};
+
+struct DevRay {
+  long long cur[3];
+  int sign[3];
+  float t_next[3], t_step[3];
+  long long steps, step;
+};
+
+// Eigen Quaternion::_transformVector (general q)
+__device__ __forceinline__ void quat_rotate(const float q[4], const float v[3], float o[3]) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  float uv0 = y * v[2] - z * v[1], uv1 = z * v[0] - x * v[2], uv2 = x * v[1] - y * v[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  const float c0 = y * uv2 - z * uv1, c1 = z * uv0 - x * uv2, c2 = x * uv1 - y * uv0;
+  o[0] = (v[0] + w * uv0) + c0;
+  o[1] = (v[1] + w * uv1) + c1;
+  o[2] = (v[2] + w * uv2) + c2;
+}
+
+__device__ __forceinline__ void ray_setup(DevRay& rc, const float s[3], const float e[3]) {
+  rc.step = 0;
+  if (isnan(s[0]) || isnan(s[1]) || isnan(s[2]) || isnan(e[0]) || isnan(e[1]) || isnan(e[2])) {
+    rc.steps = -1;
+    return;
+  }
+  rc.steps = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    rc.cur[a] = (long long)floorf(s[a] + VGX_EPS);
+    const long long end = (long long)floorf(e[a] + VGX_EPS);
+    const long long d = end - rc.cur[a];
+    rc.steps += d < 0 ? -d : d;
+    const float ray = e[a] - s[a];
+    rc.sign[a] = (ray > 0.f) - (ray < 0.f);
+    const int corrected = rc.sign[a] > 0 ? rc.sign[a] : 0;
+    const float shifted = s[a] - (float)rc.cur[a];
+    const float dist = (float)corrected - shifted;
+    if (ray == 0.f) {
+      rc.t_next[a] = 2.0f;
+      rc.t_step[a] = 2.0f;
+    } else {
+      rc.t_next[a] = dist / ray;
+      rc.t_step[a] = (float)rc.sign[a] / ray;
+    }
+  }
+}
+
+__device__ __forceinline__ bool ray_next(DevRay& rc, long long g[3]) {
+  if (rc.step++ > rc.steps) return false;
+  g[0] = rc.cur[0]; g[1] = rc.cur[1]; g[2] = rc.cur[2];
+  // minCoeff: first strictly smallest
+  const float t0 = rc.t_next[0], t1 = rc.t_next[1], t2 = rc.t_next[2];
+  if (t1 < t0) {
+    if (t2 < t1) { rc.cur[2] += rc.sign[2]; rc.t_next[2] = t2 + rc.t_step[2]; }
+    else { rc.cur[1] += rc.sign[1]; rc.t_next[1] = t1 + rc.t_step[1]; }
+  } else {
+    if (t2 < t0) { rc.cur[2] += rc.sign[2]; rc.t_next[2] = t2 + rc.t_step[2]; }
+    else { rc.cur[0] += rc.sign[0]; rc.t_next[0] = t0 + rc.t_step[0]; }
+  }
+  return true;
+}
+
+// isPointValid + transform + RayCaster ctor. Returns false for skipped points.
+__device__ __forceinline__ bool point_to_ray(const TsdfParams& P, const float* __restrict__ pts, int i,
+                                             DevRay& rc, float origin[3], float pG[3], float& weight) {
+  const float pC[3] = {pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2]};
+  const float ray_distance = sqrtf(pC[0] * pC[0] + pC[1] * pC[1] + pC[2] * pC[2]);
+  bool clearing = false;
+  if (ray_distance < P.cfg.min_ray_length_m) return false;
+  if (ray_distance > P.cfg.max_ray_length_m) {
+    if (P.cfg.allow_clear) clearing = true;
+    else return false;
+  }
+  if (!(ray_distance == ray_distance)) return false;  // NaN point
+  origin[0] = P.t[0]; origin[1] = P.t[1]; origin[2] = P.t[2];
+  float r[3];
+  quat_rotate(P.q, pC, r);
+  pG[0] = r[0] + P.t[0]; pG[1] = r[1] + P.t[1]; pG[2] = r[2] + P.t[2];
+  // getVoxelWeight
+  if (P.cfg.use_const_weight) weight = 1.0f;
+  else {
+    const float dz = fabsf(pC[2]);
+    weight = dz > VGX_EPS ? 1.0f / (dz * dz) : 0.0f;
+  }
+  const float d[3] = {pG[0] - origin[0], pG[1] - origin[1], pG[2] - origin[2]};
+  const float norm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  float u[3] = {d[0], d[1], d[2]};
+  if (norm > 0.f) { u[0] = d[0] / norm; u[1] = d[1] / norm; u[2] = d[2] / norm; }
+  const float trunc = P.cfg.default_truncation_distance;
+  float rs[3], re[3];
+  if (clearing) {
+    float len = norm - trunc;
+    if (len < 0.f) len = 0.f;
+    if (len > P.cfg.max_ray_length_m) len = P.cfg.max_ray_length_m;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      re[a] = origin[a] + u[a] * len;
+      rs[a] = P.cfg.voxel_carving_enabled ? origin[a] : re[a];
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      re[a] = pG[a] + u[a] * trunc;
+      rs[a] = P.cfg.voxel_carving_enabled ? origin[a] : (pG[a] - u[a] * trunc);
+    }
+  }
+  const float ss[3] = {rs[0] * P.voxel_size_inv, rs[1] * P.voxel_size_inv, rs[2] * P.voxel_size_inv};
+  const float es[3] = {re[0] * P.voxel_size_inv, re[1] * P.voxel_size_inv, re[2] * P.voxel_size_inv};
+  if (P.cfg.mode == 1) ray_setup(rc, es, ss);  // Fast: cast_from_origin = false
+  else ray_setup(rc, ss, es);
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long any_index_hash64(long long x, long long y, long long z) {
+  return (unsigned long long)x + (unsigned long long)y * 17191ull +
+         (unsigned long long)z * (17191ull * 17191ull);
+}
+
+// Fast scheduling: start-voxel de-duplication at start_voxel_subsampling_factor x resolution.
+__device__ __forceinline__ bool fast_start_ok(const TsdfParams& P, const float pG[3],
+                                              unsigned long long* start_set) {
+  const float inv = P.cfg.start_voxel_subsampling_factor * P.voxel_size_inv;
+  const long long k0 = (long long)floorf(pG[0] * inv + VGX_EPS);
+  const long long k1 = (long long)floorf(pG[1] * inv + VGX_EPS);
+  const long long k2 = (long long)floorf(pG[2] * inv + VGX_EPS);
+  const unsigned long long h = any_index_hash64(k0, k1, k2);
+  const unsigned long long old = atomicExch(start_set + (h & ((1ull << 20) - 1)), h);
+  return old != h;
+}
+
+// ------------------------------------------------------------------ pass 1: allocate
+__global__ void __launch_bounds__(128)
+tsdf_allocate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
+                     int32_t* __restrict__ block_idx, int* __restrict__ counters, int capacity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  DevRay rc;
+  float origin[3], pG[3], weight;
+  if (!point_to_ray(P, pts, i, rc, origin, pG, weight)) return;
+  long long g[3];
+  int lb0 = INT_MIN, lb1 = 0, lb2 = 0;
+  while (ray_next(rc, g)) {
+    const int b0 = (int)(g[0] >> P.vps_shift), b1 = (int)(g[1] >> P.vps_shift),
+              b2 = (int)(g[2] >> P.vps_shift);
+    if (b0 == lb0 && b1 == lb1 && b2 == lb2) continue;
+    lb0 = b0; lb1 = b1; lb2 = b2;
+    const uint64_t key = vgx_pack_key(b0, b1, b2);
+    uint32_t h = vgx_hash_index(b0, b1, b2, hash.mask);
+    for (;;) {
+      const uint64_t k = *((volatile uint64_t*)(hash.keys + h));
+      if (k == key) break;
+      if (k == VGX_EMPTY_KEY) {
+        const unsigned long long prev = atomicCAS((unsigned long long*)(hash.keys + h),
+                                                  (unsigned long long)VGX_EMPTY_KEY,
+                                                  (unsigned long long)key);
+        if (prev == VGX_EMPTY_KEY) {
+          const int slot = atomicAdd(counters, 1);
+          if (slot < capacity) {
+            block_idx[3 * slot] = b0; block_idx[3 * slot + 1] = b1; block_idx[3 * slot + 2] = b2;
+            hash.vals[h] = slot;
+          } else {
+            counters[1] = 1;  // overflow: block stays unmapped (vals == -1)
+          }
+          break;
+        }
+        if (prev == key) break;
+      }
+      h = (h + 1) & hash.mask;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pass 2: integrate
+__device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const float origin[3],
+                                                  const float pG[3], const long long g[3],
+                                                  float weight, float2* voxel) {
+  const float vs = P.voxel_size;
+  const float c0 = ((float)g[0] + 0.5f) * vs, c1 = ((float)g[1] + 0.5f) * vs, c2 = ((float)g[2] + 0.5f) * vs;
+  const float vv0 = c0 - origin[0], vv1 = c1 - origin[1], vv2 = c2 - origin[2];
+  const float vp0 = pG[0] - origin[0], vp1 = pG[1] - origin[1], vp2 = pG[2] - origin[2];
+  const float dist_G = sqrtf(vp0 * vp0 + vp1 * vp1 + vp2 * vp2);
+  const float dot = vv0 * vp0 + vv1 * vp1 + vv2 * vp2;
+  const float dist_G_V = dot / dist_G;
+  const float sdf = dist_G - dist_G_V;
+  float uw = weight;
+  const float trunc = P.cfg.default_truncation_distance;
+  const float dropoff_eps = vs;
+  if (P.cfg.use_weight_dropoff && sdf < -dropoff_eps) {
+    uw = weight * (trunc + sdf) / (trunc - dropoff_eps);
+    uw = uw > 0.0f ? uw : 0.0f;
+  }
+  if (P.cfg.use_sparsity_compensation_factor) {
+    if (fabsf(sdf) < trunc) uw *= P.cfg.sparsity_compensation_factor;
+  }
+  unsigned long long* addr = (unsigned long long*)voxel;
+  unsigned long long old = *((volatile unsigned long long*)addr);
+  for (;;) {
+    const float vd = __uint_as_float((unsigned)(old & 0xffffffffull));
+    const float vw = __uint_as_float((unsigned)(old >> 32));
+    const float new_weight = vw + uw;
+    if (new_weight < VGX_EPS) return;
+    const float new_sdf = (sdf * uw + vd * vw) / new_weight;
+    const float nd = (new_sdf > 0.0f) ? fminf(trunc, new_sdf) : fmaxf(-trunc, new_sdf);
+    const float nw = fminf(P.cfg.max_weight, new_weight);
+    const unsigned long long nv =
+        (unsigned long long)__float_as_uint(nd) | ((unsigned long long)__float_as_uint(nw) << 32);
+    const unsigned long long prev = atomicCAS(addr, old, nv);
+    if (prev == old) return;
+    old = prev;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+tsdf_integrate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
+                      float2* __restrict__ dw, unsigned long long* __restrict__ stats,
+                      unsigned long long* __restrict__ start_set,
+                      unsigned long long* __restrict__ obs_set) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_valid = 0, n_cast = 0, n_upd = 0;
+  if (i < P.n) {
+    DevRay rc;
+    float origin[3], pG[3], weight;
+    if (point_to_ray(P, pts, i, rc, origin, pG, weight)) {
+      n_valid = 1;
+      bool cast = true;
+      if (P.cfg.mode == 1) cast = fast_start_ok(P, pG, start_set);
+      if (cast) {
+        n_cast = 1;
+        long long g[3];
+        int lb0 = INT_MIN, lb1 = 0, lb2 = 0, slot = -1;
+        long long collisions = 0;
+        const int vmask = P.vps - 1, sh = P.vps_shift;
+        const size_t vpb = (size_t)1 << (3 * sh);
+        while (ray_next(rc, g)) {
+          if (P.cfg.mode == 1) {
+            const unsigned long long h = any_index_hash64(g[0], g[1], g[2]);
+            const unsigned long long old = atomicExch(obs_set + (h & ((1ull << 20) - 1)), h);
+            if (old == h) ++collisions; else collisions = 0;
+            if (collisions > P.cfg.max_consecutive_ray_collisions) break;
+          }
+          const int b0 = (int)(g[0] >> sh), b1 = (int)(g[1] >> sh), b2 = (int)(g[2] >> sh);
+          if (!(b0 == lb0 && b1 == lb1 && b2 == lb2)) {
+            lb0 = b0; lb1 = b1; lb2 = b2;
+            slot = vgx_hash_find(hash, b0, b1, b2);
+          }
+          if (slot < 0) continue;  // capacity overflow in pass 1
+          const int lin = (int)(g[0] & vmask) + (((int)(g[1] & vmask)) << sh) + (((int)(g[2] & vmask)) << (2 * sh));
+          update_tsdf_voxel(P, origin, pG, g, weight, dw + (size_t)slot * vpb + lin);
+          ++n_upd;
+        }
+      }
+    }
+  }
+  // warp-aggregated statistics
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_valid += __shfl_xor_sync(0xffffffffu, n_valid, off);
+    n_cast += __shfl_xor_sync(0xffffffffu, n_cast, off);
+    n_upd += __shfl_xor_sync(0xffffffffu, n_upd, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_valid) atomicAdd(stats + 0, n_valid);
+    if (n_cast) atomicAdd(stats + 1, n_cast);
+    if (n_upd) atomicAdd(stats + 2, n_upd);
+  }
+}
+
+// ------------------------------------------------------------------ C-ABI: b3
+extern "C" void vgx_tsdf_config_default(vgx_tsdf_config* c) {
+  if (!c) return;
+  // voxblox defaults overridden by voxgraph/config/voxgraph_mapper.yaml:21-28
+  c->default_truncation_distance = 0.6f;
+  c->max_weight = 10000.0f;
+  c->voxel_carving_enabled = 1;
+  c->min_ray_length_m = 0.1f;
+  c->max_ray_length_m = 16.0f;
+  c->use_const_weight = 1;
+  c->allow_clear = 1;
+  c->use_weight_dropoff = 1;
+  c->use_sparsity_compensation_factor = 1;
+  c->sparsity_compensation_factor = 20.0f;
+  c->start_voxel_subsampling_factor = 2.0f;
+  c->max_consecutive_ray_collisions = 2;
+  c->mode = 0;
+}
+
+extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7], int n,
+                                  const float* points_C, const uint8_t* rgba,
+                                  const vgx_tsdf_config* cfg, vgx_tsdf_stats* stats) {
+  (void)rgba;  // colour is only used by mesh visualisation in voxgraph; not stored
+  if (!c || !T_G_C || n < 0 || (n > 0 && !points_C)) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_tsdf_integrate: unknown submap");
+  if (s->finished) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_tsdf_integrate: submap is finished");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  vgx_tsdf_config dc;
+  vgx_tsdf_config_default(&dc);
+  TsdfParams P;
+  memset(&P, 0, sizeof(P));
+  P.cfg = cfg ? *cfg : dc;
+  if (P.cfg.mode != 0 && P.cfg.mode != 1) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_tsdf_integrate: invalid mode");
+  for (int k = 0; k < 4; ++k) P.q[k] = T_G_C[k];
+  for (int k = 0; k < 3; ++k) P.t[k] = T_G_C[4 + k];
+  P.voxel_size = s->voxel_size;
+  P.voxel_size_inv = s->voxel_size_inv;
+  P.vps = s->vps;
+  P.vps_shift = 0;
+  while ((1 << P.vps_shift) < s->vps) P.vps_shift++;
+  P.n = n;
+  vgx_tsdf_stats st;
+  memset(&st, 0, sizeof(st));
+  if (n == 0) {
+    if (stats) *stats = st;
+    return VGX_OK;
+  }
+  // scratch: points | stats[4] | (fast) two 2^20-entry approximate sets
+  const size_t pts_bytes = ((sizeof(float) * 3 * (size_t)n) + 255) & ~(size_t)255;
+  const size_t set_bytes = sizeof(unsigned long long) << 20;
+  const size_t need = pts_bytes + 256 + (P.cfg.mode == 1 ? 2 * set_bytes : 0);
+  int rc = c->ensure_scratch(need);
+  if (rc != VGX_OK) return rc;
+  char* base = (char*)c->d_scratch;
+  float* d_pts = (float*)base;
+  unsigned long long* d_stats = (unsigned long long*)(base + pts_bytes);
+  unsigned long long* d_start = (unsigned long long*)(base + pts_bytes + 256);
+  unsigned long long* d_obs = d_start + (1u << 20);
+  cudaStream_t stream = c->stream;
+  VGX_CUDA(c, cudaMemcpyAsync(d_pts, points_C, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, stream));
+  VGX_CUDA(c, cudaMemsetAsync(d_stats, 0, 256, stream));
+  if (P.cfg.mode == 1) VGX_CUDA(c, cudaMemsetAsync(d_start, 0xff, 2 * set_bytes, stream));
+  const int blocks_before = s->n_blocks;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  {
+    VgxLaunchScope scope(c, 3);
+    TsdfParams Pa = P;
+    tsdf_allocate_kernel<<<grid, 128, 0, stream>>>(Pa, d_pts, s->hash, s->d_block_idx, s->d_counters,
+                                                  s->cap_blocks);
+  }
+  {
+    VgxLaunchScope scope(c, 2);
+    tsdf_integrate_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, s->d_dw, d_stats, d_start, d_obs);
+  }
+  VGX_CUDA(c, cudaGetLastError());
+  unsigned long long h_stats[4];
+  int h_counters[2];
+  VGX_CUDA(c, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+  VGX_CUDA(c, cudaMemcpyAsync(h_counters, s->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
+  VGX_CUDA(c, cudaStreamSynchronize(stream));
+  const bool overflow = h_counters[1] != 0 || h_counters[0] > s->cap_blocks;
+  s->n_blocks = h_counters[0] < s->cap_blocks ? h_counters[0] : s->cap_blocks;
+  st.rays_valid = (int64_t)h_stats[0];
+  st.rays_cast = (int64_t)h_stats[1];
+  st.voxel_updates = (int64_t)h_stats[2];
+  st.blocks_allocated = s->n_blocks - blocks_before;
+  if (stats) *stats = st;
+  if (overflow) {
+    int fixed[2] = {s->n_blocks, 0};
+    cudaMemcpyAsync(s->d_counters, fixed, sizeof(fixed), cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
+    VGX_FAIL(c, VGX_ERR_CAPACITY, "vgx_tsdf_integrate: submap block capacity exhausted");
+  }
+  return VGX_OK;
+}

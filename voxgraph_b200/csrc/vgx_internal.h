@@ -1,0 +1,153 @@
+// Internal declarations shared by the translation units of libvoxgraph_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "voxgraph_b200.h"
+
+// ------------------------------------------------------------------ error handling
+#define VGX_CUDA(ctx, expr)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+      return VGX_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define VGX_FAIL(ctx, code, msg) \
+  do {                           \
+    (ctx)->set_error(msg);       \
+    return (code);               \
+  } while (0)
+
+// ------------------------------------------------------------------ block hash
+// voxblox AnyIndexHash (block_hash.h): x + 17191*y + 17191^2*z, then masked into an
+// open-addressing table with linear probing. Keys pack the three 21-bit biased indices.
+#define VGX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+__host__ __device__ __forceinline__ uint64_t vgx_pack_key(int bx, int by, int bz) {
+  return ((uint64_t)((uint32_t)(bx + (1 << 20)) & 0x1FFFFFu)) |
+         ((uint64_t)((uint32_t)(by + (1 << 20)) & 0x1FFFFFu) << 21) |
+         ((uint64_t)((uint32_t)(bz + (1 << 20)) & 0x1FFFFFu) << 42);
+}
+__host__ __device__ __forceinline__ uint32_t vgx_hash_index(int bx, int by, int bz, uint32_t mask) {
+  uint64_t h = (uint64_t)(int64_t)bx + (uint64_t)(int64_t)by * 17191ull +
+               (uint64_t)(int64_t)bz * (17191ull * 17191ull);
+  h ^= h >> 15;  // fold the high bits so power-of-two masking sees all three axes
+  return (uint32_t)h & mask;
+}
+
+struct VgxHash {
+  uint64_t* keys;   // VGX_EMPTY_KEY when free
+  int32_t* vals;    // brick slot
+  uint32_t mask;    // table_size - 1
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int vgx_hash_find(const VgxHash& h, int bx, int by, int bz) {
+  const uint64_t key = vgx_pack_key(bx, by, bz);
+  uint32_t i = vgx_hash_index(bx, by, bz, h.mask);
+  for (;;) {
+    const uint64_t k = __ldg(h.keys + i);
+    if (k == key) return __ldg(h.vals + i);
+    if (k == VGX_EMPTY_KEY) return -1;
+    i = (i + 1) & h.mask;
+  }
+}
+#endif
+
+// ------------------------------------------------------------------ submap store
+struct VgxPoints {  // WeightedSampler<RegistrationPoint> as SoA
+  int n = 0;
+  float *x = nullptr, *y = nullptr, *z = nullptr, *dist = nullptr, *w = nullptr;
+  double sum_w = 0;  // summed_reference_weight (cpp:124), sequential double sum
+};
+
+struct VgxSubmap {
+  uint32_t id = 0;
+  float voxel_size = 0, voxel_size_inv = 0, block_size = 0, block_size_inv = 0;
+  int vps = 16, vox_per_block = 4096;
+  int cap_blocks = 0;
+  int n_blocks = 0;            // host mirror (valid after upload / integrate sync)
+  bool finished = false;
+  VgxHash hash{nullptr, nullptr, 0};
+  int32_t* d_block_idx = nullptr;  // cap x 3
+  float2* d_dw = nullptr;          // cap x vps^3 (distance, weight)
+  float* d_view = nullptr;         // cap x vps^3: distance where observed, NaN elsewhere
+  int* d_counters = nullptr;       // [0] = n_blocks (device), [1] = overflow flag
+  VgxPoints points[2];
+};
+
+// ------------------------------------------------------------------ pose graph
+struct VgxRelEdge {
+  int a, b;
+  double t_obs[3], yaw_obs, L[16];
+};
+
+struct VgxGraph;  // defined in graph.cu
+
+struct VgxProfileSlot {
+  double total_ms = 0;
+  int64_t launches = 0;
+};
+
+struct vgx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  std::map<uint32_t, VgxSubmap*> submaps;
+  VgxGraph* graph = nullptr;
+  // profiling
+  bool profile = false;
+  VgxProfileSlot prof[6];
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch
+  void* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* h_pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // NCCL
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+
+  void set_error(const std::string& e) { error = e; }
+  VgxSubmap* find(uint32_t id) {
+    auto it = submaps.find(id);
+    return it == submaps.end() ? nullptr : it->second;
+  }
+  int ensure_scratch(size_t bytes);
+  int ensure_pinned(size_t bytes);
+};
+
+// RAII-less helper to bracket kernel launches for accounting.
+struct VgxLaunchScope {
+  vgx_ctx* c;
+  int which;
+  VgxLaunchScope(vgx_ctx* ctx, int w, int n_launches = 1) : c(ctx), which(w) {
+    c->launches += n_launches;
+    c->prof[which].launches += n_launches;
+    if (c->profile) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~VgxLaunchScope() {
+    if (c->profile) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->prof[which].total_ms += ms;
+    }
+  }
+};
+
+void vgx_graph_free(vgx_ctx* ctx);
+void vgx_graph_invalidate_registration(vgx_ctx* ctx);
+
+// NCCL (dlopen'ed, nccl_dyn.cpp)
+int vgx_nccl_allreduce_sum_f64(vgx_ctx* ctx, double* d_buf, size_t count);
