@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py — registration residuals/s + pose-graph solve ms (BASELINE.json metric).
+
+A "step" is one full evaluation of the registration hot path over every registration
+constraint of the pose graph: per point transform -> 8-voxel brick gather -> trilinear
+interpolation -> residual -> two 1x4 Jacobians -> in-kernel reduction to the per-constraint
+normal-equation blocks -> assembly of the global J^T J / J^T r (+ one NCCL all-reduce for N > 1).
+
+Workload (N = 1): BASELINE.json configs[1] — 50 submaps / 200 overlapping pairs (400 mirrored
+residual blocks) / 10k isosurface points per block, 0.20 m voxels.  For N > 1 the per-GPU work
+is fixed (weak scaling): N copies of the 50-submap floor, 200*N pairs, sharded over the ranks.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference      # restated reference CPU path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_RESIDUAL = 84  # 20 B point + 8 corners x (4 B distance + 4 B weight)
+ALGO_BYTES_PER_TSDF_UPDATE = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--submaps", type=int, default=50)
+    ap.add_argument("--pairs", type=int, default=200)
+    ap.add_argument("--points", type=int, default=10000)
+    ap.add_argument("--voxel-size", type=float, default=0.2)
+    ap.add_argument("--no-extras", action="store_true", help="skip solve / TSDF / CPU baseline extras")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- workload
+def build_floor(args):
+    """One floor = BASELINE configs[1]: seeded, cached in /tmp (generation is host-side numpy)."""
+    from voxgraph_b200 import synth
+    key = "vgx_floor_s%d_p%d_k%d_v%g.npz" % (args.submaps, args.pairs, args.points, args.voxel_size)
+    path = os.path.join("/tmp", key)
+    sc = None
+    if os.path.exists(path):
+        try:
+            import pickle
+            with open(path, "rb") as f:
+                sc = pickle.load(f)
+        except Exception:
+            sc = None
+    if sc is None:
+        sc = synth.make_scene(seed=2, n_submaps=args.submaps, n_points=args.points,
+                              voxel_size=args.voxel_size, max_pairs=args.pairs,
+                              trunc=0.6 if abs(args.voxel_size - 0.2) < 1e-9 else None)
+        try:
+            import pickle
+            tmp = path + ".%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                pickle.dump(sc, f, protocol=4)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return sc
+
+
+def floors(sc, n_floors):
+    """Weak-scaled problem: n copies of the floor, shifted in the mission frame; submap ids
+    f*S + i. Returns (ids, poses_init, poses_gt, submap_of_id, pairs, odometry)."""
+    S = len(sc.submaps)
+    ids, pinit, pgt, pairs, odo = [], [], [], [], []
+    for f in range(n_floors):
+        shift = np.array([f * (sc.world.size_xy[0] + 30.0), 0.0, 0.0, 0.0])
+        for i in range(S):
+            ids.append(f * S + i)
+            pinit.append(sc.poses_init[i] + shift)
+            pgt.append(sc.poses_gt[i] + shift)
+        pairs += [(f * S + i, f * S + j) for (i, j) in sc.pairs]
+        odo += [(f * S + i, f * S + j, t, y) for (i, j, t, y) in sc.odometry]
+        if f > 0:
+            from voxgraph_b200 import synth
+            t, y = synth.relative_pose(pgt[f * S - 1], pgt[f * S])
+            odo.append((f * S - 1, f * S, t, float(y)))
+    return ids, np.array(pinit), np.array(pgt), pairs, odo
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(f) > 3 + k and f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def oracle_graph(sc, n_floors, max_residuals=None):
+    from oracle import oracle as o
+    ids, pinit, pgt, pairs, odo = floors(sc, n_floors)
+    S = len(sc.submaps)
+    layers = [o.Layer.from_blocks(s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
+              for s in sc.submaps]
+    g = o.Graph()
+    for k, i in enumerate(ids):
+        g.add_node(i, pinit[k], constant=(k == 0))
+    L = o.sqrt_information(sc.odom_information)
+    for (i, j, t, y) in odo:
+        g.add_relative(i, j, t, y, L)
+    R = 0
+    for (i, j) in pairs:
+        a, b = sc.submaps[i % S], sc.submaps[j % S]
+        g.add_registration(i, j, layers[j % S], a.points_xyz, a.points_distance, a.points_weight)
+        g.add_registration(j, i, layers[i % S], b.points_xyz, b.points_distance, b.points_weight)
+        R += 2 * a.points_xyz.shape[0]
+        if max_residuals is not None and R >= max_residuals:
+            break
+    return g, o
+
+
+def cpu_reference(sc, args, steps, warmup, budget_s):
+    """Times the restated reference CPU path (oracle) with all host threads on a bounded sample."""
+    cores = os.cpu_count() or 1
+    g, o = oracle_graph(sc, 1)
+    R = g.num_registration_residuals
+    t = time.time(); g.eval(num_threads=cores, want_H=True); one = time.time() - t
+    # bound the sample: fewer constraints if one full evaluation would blow the budget
+    sample = "all %d registration residuals of the N=1 workload per step" % R
+    if one * (steps + warmup) > budget_s and one > 0:
+        frac = max(0.02, budget_s / (one * (steps + warmup)))
+        g, o = oracle_graph(sc, 1, max_residuals=int(R * frac))
+        R = g.num_registration_residuals
+        sample = "first %d registration residuals (%.0f%% of the constraints) of the N=1 workload per step" % (
+            R, 100 * frac)
+    for _ in range(warmup):
+        g.eval(num_threads=cores, want_H=True)
+    t0 = time.time()
+    for _ in range(steps):
+        g.eval(num_threads=cores, want_H=True)
+    dt = (time.time() - t0) / steps
+    t4 = time.time(); g.eval(num_threads=min(4, cores), want_H=True); dt4 = time.time() - t4
+    return dict(value=R / dt, unit="residuals/s", cores=cores, kind="port", sample=sample,
+                ms_per_step=dt * 1e3, value_4_threads=R / dt4,
+                note="restated reference (Ceres/voxblox/Eigen absent from the image; see DESIGN.md)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = build_floor(args)
+    steps = max(1, args.steps); warmup = max(0, args.warmup)
+    cb = cpu_reference(sc, args, steps, warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": "registration_residuals_per_s", "value": cb["value"],
+            "unit": "residuals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, sc, 1),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "residuals/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, sc, n_gpus):
+    return {"workload": "BASELINE configs[1]: %d submaps / %d overlapping pairs (x2 mirrored residual "
+                        "blocks) / %d isosurface points per block, %.2f m voxels, 16^3-voxel bricks%s"
+                        % (args.submaps, len(sc.pairs), args.points, args.voxel_size,
+                           "" if n_gpus == 1 else "; x%d floors (weak scaling), constraints sharded over ranks" % n_gpus),
+            "submaps": args.submaps * n_gpus, "pairs": len(sc.pairs) * n_gpus,
+            "points_per_constraint": args.points, "voxel_size": args.voxel_size,
+            "registration_point_type": "isosurface", "sampling_ratio": -1,
+            "l2": "inputs (points + reading bricks) exceed the 126 MB L2; no explicit flush in the bracketed region",
+            "parallelism": "pairs sharded x%d, NCCL all-reduce of packed H/g blocks" % n_gpus if n_gpus > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from voxgraph_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    sc = build_floor(args)
+    ids, pinit, pgt, pairs, odo = floors(sc, n_gpus)
+    S = len(sc.submaps)
+
+    ctx = api.Context(local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.from_numpy(api.comm_unique_id()).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, uid.cpu().numpy())
+
+    t_up = time.time()
+    bricks_bytes = 0
+    for k, sid in enumerate(ids):
+        s = sc.submaps[sid % S]
+        ctx.submap_upload(sid, s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
+        ctx.submap_upload_points(sid, api.K_ISOSURFACE_POINTS, s.points_xyz, s.points_distance,
+                                 s.points_weight)
+        bricks_bytes += s.num_blocks * s.vps ** 3 * 32
+    upload_s = time.time() - t_up
+
+    pg = api.PoseGraph(ctx)
+    for k, sid in enumerate(ids):
+        pg.addSubmapNode(api.SubmapNodeConfig(sid, pinit[k], set_constant=(k == 0)))
+    for (i, j, t, y) in odo:
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(i, j, np.array([*t, y]),
+                                                                      sc.odom_information))
+    for (i, j) in pairs:
+        pg.addRegistrationConstraint(api.RegistrationConstraintConfig(i, j))
+    pg._sync()
+    r_local, r_global = ctx.graph_num_registration_residuals()
+    n_nodes = len(ids)
+
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput: K steps in one bracket
+    for _ in range(max(args.warmup, 3)):
+        ctx.graph_eval_async()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.graph_eval_async()
+        e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = r_global / (ms_step * 1e-3)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---------------- end to end through the public call with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    poses_host = pinit.copy()
+    for _ in range(2):
+        ctx.graph_set_poses(poses_host); ctx.graph_eval(n_nodes, want_H=False)
+    barrier()
+    t0 = time.time()
+    for k in range(e2e_steps):
+        poses_host[1:, 0] += 1e-6            # new poses every step (H2D inside the timed region)
+        ctx.graph_set_poses(poses_host)
+        ok, cost, g, _ = ctx.graph_eval(n_nodes, want_H=False)   # D2H of cost / gradient / H blocks
+    barrier()
+    e2e_s = (time.time() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    packed_len = 4 + 20 * n_nodes + 16 * len(set((min(a, b), max(a, b)) for (a, b) in
+                                                [(i, j) for (i, j) in pairs] + [(i, j) for (i, j, _, _) in odo]))
+    e2e = {"value": r_global / e2e_s, "unit": "residuals/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(n_nodes * 32), "d2h_bytes_per_step": int(packed_len * 8),
+           "call": "vgx_graph_set_poses + vgx_graph_eval (fused reduce mode; host poses in, host cost/gradient/H-blocks out)"}
+
+    # ---------------- roofline of the dominant kernel (per-kernel CUDA events on the ctx stream)
+    ctx.profile_reset(); ctx.profile_enable(True)
+    for _ in range(max(3, min(args.steps, 10))):
+        ctx.graph_eval_async()
+    ctx.synchronize()
+    k_ms, k_n = ctx.profile_get(0)
+    o_ms, o_n = ctx.profile_get(5)
+    ctx.profile_enable(False)
+    kern_ms = k_ms / max(k_n, 1)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (MEASURED_PEAKS.json absent)"
+    achieved = r_local * ALGO_BYTES_PER_RESIDUAL / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "reg_reduce_kernel<true>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_residual": ALGO_BYTES_PER_RESIDUAL,
+                "residuals_per_launch": int(r_local), "kernel_ms": kern_ms,
+                "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
+                "other_kernels_ms_per_step": (o_ms / max(k_n, 1))}
+    prof_traffic = os.path.join(ROOT, "profiles", "reg_reduce_traffic.json")
+    if os.path.exists(prof_traffic):
+        try:
+            roofline["traffic"] = json.load(open(prof_traffic)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    extras = {}
+    if not args.no_extras:
+        # ---------------- pose-graph solve wall time (second half of the metric)
+        solve_ms = []
+        summ = None
+        for rep in range(3):
+            ctx.graph_set_poses(pinit)
+            barrier()
+            t0 = time.time()
+            x, summ = ctx.graph_solve(n_nodes, ctx.solver_options())
+            solve_ms.append((time.time() - t0) * 1e3)
+        err0 = float(np.abs(pinit[:, :2] - pgt[:, :2]).mean())
+        err1 = float(np.abs(x[:, :2] - pgt[:, :2]).mean())
+        extras["solve"] = {"solve_ms": float(np.median(solve_ms)), "lm_iterations": summ.iterations,
+                           "successful_steps": summ.num_successful_steps,
+                           "termination": summ.termination, "initial_cost": summ.initial_cost,
+                           "final_cost": summ.final_cost,
+                           "mean_xy_error_before_m": err0, "mean_xy_error_after_m": err1,
+                           "options": "Ceres defaults + parameter_tolerance 3e-3 (pose_graph.cpp:91-97)"}
+        if rank == 0:
+            # ---------------- TSDF integration (HP1), configs[2]-shaped scan, rank 0 only
+            from voxgraph_b200 import synth
+            wpose = np.array([sc.poses_gt[0][0], sc.poses_gt[0][1], 1.2, 0.3])
+            pts = synth.lidar_scan(sc.world, wpose, n_beams=64, n_azimuth=1024, seed=3, miss_range=40.0)
+            T = synth.pose_to_T([0, 0, 0, 0])
+            cfg = ctx.tsdf_config()
+            ctx.submap_create(10 ** 6, 0.2, 16, 8192)
+            ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
+            ctx.profile_reset(); ctx.profile_enable(True)
+            reps = 5
+            t0 = time.time()
+            for _ in range(reps):
+                st = ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
+            wall = (time.time() - t0) / reps
+            ims, inn = ctx.profile_get(2); ams, ann = ctx.profile_get(3)
+            ctx.profile_enable(False)
+            kms = ims / max(inn, 1)
+            extras["tsdf"] = {"rays": int(pts.shape[0]), "voxel_updates_per_scan": int(st.voxel_updates),
+                              "integrate_kernel_ms": kms, "allocate_kernel_ms": ams / max(ann, 1),
+                              "updates_per_s_kernel": st.voxel_updates / (kms * 1e-3),
+                              "updates_per_s_e2e": st.voxel_updates / wall,
+                              "achieved_gbs": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9 / peak,
+                              "mode": "simple (every ray, every voxel), 64x1024 LiDAR, 0.20 m voxels"}
+            ctx.submap_free(10 ** 6)
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_extras:
+        cpu = cpu_reference(sc, args, steps=3, warmup=1, budget_s=args.cpu_seconds)
+        if "solve" in extras:
+            # the reference's CPU solve of the same problem, same options (bounded: <= 4 s cap each)
+            try:
+                g, o = oracle_graph(sc, 1)
+                rc, so = g.solve(o.solver_options(num_threads=min(4, os.cpu_count() or 1)))
+                extras["solve"]["cpu_reference_solve_ms"] = so.total_time_s * 1e3
+                extras["solve"]["cpu_reference_iterations"] = so.iterations
+                extras["solve"]["cpu_reference_final_cost"] = so.final_cost
+                extras["solve"]["cpu_reference_threads"] = min(4, os.cpu_count() or 1)
+                xo = g.poses()
+                extras["solve"]["max_pose_diff_vs_cpu_reference"] = float(np.abs(x - xo).max())
+            except Exception as e:  # pragma: no cover
+                extras["solve"]["cpu_reference_error"] = repr(e)
+
+    if rank == 0:
+        line = {"metric": "registration_residuals_per_s", "value": value, "unit": "residuals/s",
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, sc, n_gpus),
+                "residuals_per_step": int(r_global), "gpu_launches": int(launches),
+                "clocks": clocks, "e2e": e2e, "roofline": roofline,
+                "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                       "value_4_threads", "note")} if cpu else None),
+                "upload_s": upload_s, "resident_bytes": {"points": int(r_global // max(n_gpus, 1) * 20),
+                                                         "reading_bricks_view": int(bricks_bytes)}}
+        line.update(extras)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,64 +37,90 @@ reg_emit_kernel(RegConstraintDev C, RegPoseConst P, double* __restrict__ residua
 //   g[5]  = sum j * r,   c = sum r^2
 // The 8x8 block of the residual block follows from je[0..2] == -jr[0..2].
 
-// Warp transpose-reduce: 32 per-lane values -> lane l holds the warp total of value l.
-__device__ __forceinline__ double warp_transpose_reduce(double (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < off; ++k) {
-      const double send = hi ? v[k] : v[k + off];
-      const double keep = hi ? v[k + off] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
+// The sums are the 6x6 Gram matrix of v = (jr0, jr1, jr2, jr3, je3, r) over the points, formed
+// on the FP64 tensor cores: each warp stages its 32 points' vectors in shared memory and issues
+// eight mma.sync.m8n8k4.f64 (A = B^T = 4 points x 8 components), so the reduction over points
+// happens inside the MMA and each lane keeps just two accumulators.
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
 }
 
+#define VGX_STAGE_STRIDE 36  // doubles per component row (32 points + pad: 2-way = optimal for 8 B)
+
 template <bool kJacobian>
-__global__ void __launch_bounds__(VGX_REG_THREADS)
+__global__ void __launch_bounds__(VGX_REG_THREADS, 4)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
                   double* __restrict__ partials) {
-  __shared__ double s_part[VGX_REG_THREADS / 32][VGX_REG_NSUM];
+  constexpr int kWarps = VGX_REG_THREADS / 32;
+  __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
+  __shared__ double s_gram[kWarps][64];
   const RegTile T = tiles[blockIdx.x];
   const RegConstraintDev C = constraints[T.constraint];
   const RegPoseConst P = poses[T.constraint];
-  double acc[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 2, tig = lane & 3;
+  double d0 = 0.0, d1 = 0.0;
 
   const int end = T.start + T.count;
-  for (int i = T.start + threadIdx.x; i < end; i += VGX_REG_THREADS) {
-    const float xi = __ldg(C.px + i), yi = __ldg(C.py + i), zi = __ldg(C.pz + i);
-    const float dist = __ldg(C.pd + i), w = __ldg(C.pw + i);
-    const RegPointResult R = vgx_reg_point<kJacobian>(C, P, xi, yi, zi, dist, w);
-    acc[20] = fma(R.r, R.r, acc[20]);
+  for (int base = T.start; base < end; base += VGX_REG_THREADS) {
+    const int i = base + threadIdx.x;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+    if (i < end) {
+      const float xi = __ldg(C.px + i), yi = __ldg(C.py + i), zi = __ldg(C.pz + i);
+      const float dist = __ldg(C.pd + i), w = __ldg(C.pw + i);
+      const RegPointResult R = vgx_reg_point<kJacobian>(C, P, xi, yi, zi, dist, w);
+      v5 = R.r;
+      if (kJacobian) {
+        v0 = (double)R.jr[0]; v1 = (double)R.jr[1]; v2 = (double)R.jr[2];
+        v3 = (double)R.jr[3]; v4 = (double)R.je3;
+      }
+    }
     if (kJacobian) {
-      const double j0 = (double)R.jr[0], j1 = (double)R.jr[1], j2 = (double)R.jr[2],
-                   j3 = (double)R.jr[3], j4 = (double)R.je3;
-      acc[0] = fma(j0, j0, acc[0]); acc[1] = fma(j0, j1, acc[1]); acc[2] = fma(j0, j2, acc[2]);
-      acc[3] = fma(j0, j3, acc[3]); acc[4] = fma(j0, j4, acc[4]);
-      acc[5] = fma(j1, j1, acc[5]); acc[6] = fma(j1, j2, acc[6]); acc[7] = fma(j1, j3, acc[7]);
-      acc[8] = fma(j1, j4, acc[8]);
-      acc[9] = fma(j2, j2, acc[9]); acc[10] = fma(j2, j3, acc[10]); acc[11] = fma(j2, j4, acc[11]);
-      acc[12] = fma(j3, j3, acc[12]); acc[13] = fma(j3, j4, acc[13]);
-      acc[14] = fma(j4, j4, acc[14]);
-      acc[15] = fma(j0, R.r, acc[15]); acc[16] = fma(j1, R.r, acc[16]);
-      acc[17] = fma(j2, R.r, acc[17]); acc[18] = fma(j3, R.r, acc[18]);
-      acc[19] = fma(j4, R.r, acc[19]);
+      s_stage[warp][0][lane] = v0; s_stage[warp][1][lane] = v1; s_stage[warp][2][lane] = v2;
+      s_stage[warp][3][lane] = v3; s_stage[warp][4][lane] = v4; s_stage[warp][5][lane] = v5;
+      __syncwarp();
+#pragma unroll
+      for (int t4 = 0; t4 < 8; ++t4) {
+        const double a = (grp < 6) ? s_stage[warp][grp][4 * t4 + tig] : 0.0;
+        dmma_8x8x4(d0, d1, a, a);
+      }
+      __syncwarp();
+    } else {
+      d0 = fma(v5, v5, d0);
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double tot = warp_transpose_reduce(acc, lane);
-  if (lane < VGX_REG_NSUM) s_part[warp][lane] = tot;
+  if (kJacobian) {
+    s_gram[warp][grp * 8 + 2 * tig] = d0;
+    s_gram[warp][grp * 8 + 2 * tig + 1] = d1;
+  } else {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, off);
+    if (lane == 0) s_gram[warp][0] = d0;
+  }
   __syncthreads();
   if (threadIdx.x < VGX_REG_NSUM) {
+    // entry e of the 21 sums -> (row, col) of the Gram matrix
+    int row = 5, col = 5;
+    const int e = threadIdx.x;
+    if (e < 15) {
+      int p = 0, rem = e;
+      while (rem >= 5 - p) { rem -= 5 - p; ++p; }
+      row = p; col = p + rem;
+    } else if (e < 20) {
+      row = e - 15; col = 5;
+    }
     double s = 0;
+    if (kJacobian) {
 #pragma unroll
-    for (int wv = 0; wv < VGX_REG_THREADS / 32; ++wv) s += s_part[wv][threadIdx.x];
-    partials[(size_t)blockIdx.x * VGX_REG_NSTRIDE + threadIdx.x] = s;
+      for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][row * 8 + col];
+    } else if (e == 20) {
+#pragma unroll
+      for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
+    }
+    partials[(size_t)blockIdx.x * VGX_REG_NSTRIDE + e] = s;
   }
 }
 

@@ -28,7 +28,7 @@ struct RegConstraintDev {
   int n;
   int ref_node, read_node;
   VgxHash hash;        // reading submap block hash
-  const float* view;   // reading bricks: distance, NaN where unobserved
+  const float* view;   // reading octets: 8 floats per voxel, NaN where unobserved / missing
   float voxel_size, voxel_size_inv, block_size, block_size_inv;
   int vps, vps_shift;
   double factor;       // num_residuals / summed_reference_weight (cpp:274)
@@ -123,9 +123,14 @@ struct RegPointResult {
   bool ok;         // interpolation possible
 };
 
-__device__ __forceinline__ int vgx_floor_idx(float v) { return (int)floorf(v); }
+// floor(v) as int: single F2I.FLOOR (== (int)floorf(v) for in-range v).
+__device__ __forceinline__ int vgx_floor_idx(float v) { return __float2int_rd(v); }
 
-// getVoxelsAndQVector: returns false when a block is missing or a corner unobserved.
+// getVoxelsAndQVector on the octet view: locate the base corner voxel (the one whose centre
+// is <= pos on every axis, possibly in the lower neighbour block), fetch its 2x2x2 octet with
+// two 128-bit loads. Returns false when the base block is missing or any corner is
+// unobserved / in a missing block (NaN baked into the view).  The reference's first lookup of
+// the block containing pos is implied: that block always holds one of the 8 corners.
 __device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, float p0, float p1,
                                                   float p2, float d[8], float& ox, float& oy,
                                                   float& oz) {
@@ -133,8 +138,6 @@ __device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, flo
   int b0 = vgx_floor_idx(p0 * C.block_size_inv + VGX_COORD_EPS);
   int b1 = vgx_floor_idx(p1 * C.block_size_inv + VGX_COORD_EPS);
   int b2 = vgx_floor_idx(p2 * C.block_size_inv + VGX_COORD_EPS);
-  int slot = vgx_hash_find(C.hash, b0, b1, b2);
-  if (slot < 0) return false;
   const float or0 = (float)b0 * C.block_size, or1 = (float)b1 * C.block_size,
               or2 = (float)b2 * C.block_size;
   int v0 = vgx_floor_idx((p0 - or0) * C.voxel_size_inv + VGX_COORD_EPS);
@@ -143,68 +146,31 @@ __device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, flo
   v0 = max(min(v0, vps - 1), 0);
   v1 = max(min(v1, vps - 1), 0);
   v2 = max(min(v2, vps - 1), 0);
-  bool moved = false;
   if (p0 - (or0 + ((float)v0 + 0.5f) * C.voxel_size) < 0) {
-    if (--v0 < 0) { --b0; v0 += vps; moved = true; }
+    if (--v0 < 0) { --b0; v0 += vps; }
   }
   if (p1 - (or1 + ((float)v1 + 0.5f) * C.voxel_size) < 0) {
-    if (--v1 < 0) { --b1; v1 += vps; moved = true; }
+    if (--v1 < 0) { --b1; v1 += vps; }
   }
   if (p2 - (or2 + ((float)v2 + 0.5f) * C.voxel_size) < 0) {
-    if (--v2 < 0) { --b2; v2 += vps; moved = true; }
+    if (--v2 < 0) { --b2; v2 += vps; }
   }
-  if (moved) {
-    slot = vgx_hash_find(C.hash, b0, b1, b2);
-    if (slot < 0) return false;
-  }
+  const int slot = vgx_hash_find(C.hash, b0, b1, b2);
+  if (slot < 0) return false;
   // q vector offsets from the base corner (block origin recomputed from the moved index)
   ox = (p0 - ((float)b0 * C.block_size + ((float)v0 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
   oy = (p1 - ((float)b1 * C.block_size + ((float)v1 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
   oz = (p2 - ((float)b2 * C.block_size + ((float)v2 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
-
-  const bool c0 = (v0 == vps - 1), c1 = (v1 == vps - 1), c2 = (v2 == vps - 1);
   const int sh = C.vps_shift;
-  const size_t vpb = (size_t)1 << (3 * sh);
-  const int x0 = v0, x1 = (v0 + 1) & (vps - 1);
-  const int yy0 = v1 << sh, yy1 = ((v1 + 1) & (vps - 1)) << sh;
-  const int zz0 = v2 << (2 * sh), zz1 = ((v2 + 1) & (vps - 1)) << (2 * sh);
-  if (!(c0 | c1 | c2)) {
-    const float* base = C.view + (size_t)slot * vpb;
-    // corner i: x = bit2, y = bit1, z = bit0
-    d[0] = __ldg(base + x0 + yy0 + zz0);
-    d[1] = __ldg(base + x0 + yy0 + zz1);
-    d[2] = __ldg(base + x0 + yy1 + zz0);
-    d[3] = __ldg(base + x0 + yy1 + zz1);
-    d[4] = __ldg(base + x1 + yy0 + zz0);
-    d[5] = __ldg(base + x1 + yy0 + zz1);
-    d[6] = __ldg(base + x1 + yy1 + zz0);
-    d[7] = __ldg(base + x1 + yy1 + zz1);
-  } else {
-    int s[8];
-    s[0] = slot;
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      const bool ux = (i & 4) && c0, uy = (i & 2) && c1, uz = (i & 1) && c2;
-      // a corner that stays inside the base block in every crossing axis reuses an earlier slot
-      const int j = (ux ? 4 : 0) | (uy ? 2 : 0) | (uz ? 1 : 0);
-      if (j == i) {
-        s[i] = vgx_hash_find(C.hash, b0 + (ux ? 1 : 0), b1 + (uy ? 1 : 0), b2 + (uz ? 1 : 0));
-        if (s[i] < 0) return false;
-      } else {
-        s[i] = s[j];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int lin = ((i & 4) ? x1 : x0) + ((i & 2) ? yy1 : yy0) + ((i & 1) ? zz1 : zz0);
-      d[i] = __ldg(C.view + (size_t)s[i] * vpb + lin);
-    }
-  }
-  // isObservedVoxel failed <=> NaN in the view
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ok = ok && (d[i] == d[i]);
-  return ok;
+  const size_t lin = ((size_t)slot << (3 * sh)) + v0 + (v1 << sh) + (v2 << (2 * sh));
+  const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
+  const float4 lo = __ldg(o), hi = __ldg(o + 1);
+  d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w;
+  d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
+  // isObservedVoxel failed / block missing <=> NaN in the octet: the sum is NaN iff any is
+  const float chk = ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+  return chk == chk || !(isnan(d[0]) || isnan(d[1]) || isnan(d[2]) || isnan(d[3]) || isnan(d[4]) ||
+                         isnan(d[5]) || isnan(d[6]) || isnan(d[7]));
 }
 
 template <bool kJacobian>
@@ -243,12 +209,14 @@ __device__ __forceinline__ RegPointResult vgx_reg_point(const RegConstraintDev& 
   R.r = ((double)dist - (double)interp) * (double)w;  // cpp:158-163
   if (kJacobian) {
     // cpp:183-202: double deltas, float entries
-    const double inv = (double)C.voxel_size_inv;
+    // (float)(inv * Dx): the double product of two floats is exact, so rounding it to float
+    // is the float product; the triple products round once in double first, kept in double.
+    const float finv = C.voxel_size_inv;
+    const float iDx = finv * q[1], iDy = finv * q[2], iDz = finv * q[3];
+    const double inv = (double)finv;
     const double Dx = (double)q[1], Dy = (double)q[2], Dz = (double)q[3];
-    const float finv = (float)inv;
-    const float iDx = (float)(inv * Dx), iDy = (float)(inv * Dy), iDz = (float)(inv * Dz);
-    const float iDyDz = (float)(inv * Dy * Dz), iDxDz = (float)(inv * Dx * Dz),
-                iDxDy = (float)(inv * Dx * Dy);
+    const double iDyd = inv * Dy, iDxd = inv * Dx;
+    const float iDyDz = (float)(iDyd * Dz), iDxDz = (float)(iDxd * Dz), iDxDy = (float)(iDxd * Dy);
     // cpp:204-205: pInterp_pr = a * pQ_pr summed k = 0..7; the structurally zero entries of
     // pQ_pr add (+-0) and are skipped (value-identical)
     float g0 = a[1] * finv;

@@ -63,8 +63,7 @@ static void free_points(VgxPoints& p) {
 
 static void free_submap(VgxSubmap* s) {
   if (!s) return;
-  cudaFree(s->hash.keys);
-  cudaFree(s->hash.vals);
+  cudaFree(s->hash.entries);
   cudaFree(s->d_block_idx);
   cudaFree(s->d_dw);
   cudaFree(s->d_view);
@@ -117,11 +116,14 @@ extern "C" int vgx_profile_get(vgx_ctx* c, int which, double* total_ms, int64_t*
 extern "C" int64_t vgx_launch_count(vgx_ctx* c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------ kernels
-__global__ void hash_clear_kernel(uint64_t* keys, int32_t* vals, uint32_t size) {
+__global__ void hash_clear_kernel(VgxHashEntry* entries, uint32_t size) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < size) {
-    keys[i] = VGX_EMPTY_KEY;
-    vals[i] = -1;
+    VgxHashEntry e;
+    e.key = VGX_EMPTY_KEY;
+    e.val = -1;
+    e.pad = 0;
+    entries[i] = e;
   }
 }
 
@@ -134,32 +136,62 @@ __global__ void hash_insert_kernel(VgxHash h, const int32_t* block_idx, int n) {
   uint32_t i = vgx_hash_index(bx, by, bz, h.mask);
   for (;;) {
     unsigned long long prev =
-        atomicCAS((unsigned long long*)(h.keys + i), (unsigned long long)VGX_EMPTY_KEY,
+        atomicCAS((unsigned long long*)&h.entries[i].key, (unsigned long long)VGX_EMPTY_KEY,
                   (unsigned long long)key);
     if (prev == VGX_EMPTY_KEY || prev == key) {
-      h.vals[i] = s;  // duplicates in the input: last writer wins
+      h.entries[i].val = s;  // duplicates in the input: last writer wins
       return;
     }
     i = (i + 1) & h.mask;
   }
 }
 
-// (distance[], weight[]) -> interleaved float2 bricks + registration view.
+// (distance[], weight[]) -> interleaved float2 bricks.
 __global__ void interleave_kernel(const float* __restrict__ d, const float* __restrict__ w,
-                                  float2* __restrict__ dw, float* __restrict__ view, size_t n) {
+                                  float2* __restrict__ dw, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float dd = d[i], ww = w[i];
-  dw[i] = make_float2(dd, ww);
-  // utils::isObservedVoxel: weight > 1e-6
-  view[i] = (ww > 1e-6f) ? dd : __int_as_float(0x7fc00000);
+  dw[i] = make_float2(d[i], w[i]);
 }
 
-__global__ void build_view_kernel(const float2* __restrict__ dw, float* __restrict__ view, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float2 v = dw[i];
-  view[i] = (v.y > 1e-6f) ? v.x : __int_as_float(0x7fc00000);
+// Registration view: one thread per voxel gathers its 2x2x2 forward neighbourhood (across
+// brick faces through the hash) and stores the 8 distances, NaN where
+// utils::isObservedVoxel (weight > 1e-6) fails or the neighbour block does not exist.
+__global__ void __launch_bounds__(256)
+build_view_kernel(const float2* __restrict__ dw, const int32_t* __restrict__ block_idx, VgxHash hash,
+                  float* __restrict__ view, int n_blocks, int vps, int sh) {
+  const size_t vpb = (size_t)1 << (3 * sh);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n_blocks * vpb) return;
+  const int slot = (int)(i >> (3 * sh));
+  const int lin = (int)(i & (vpb - 1));
+  const int vx = lin & (vps - 1), vy = (lin >> sh) & (vps - 1), vz = lin >> (2 * sh);
+  const int bx = block_idx[3 * slot], by = block_idx[3 * slot + 1], bz = block_idx[3 * slot + 2];
+  const bool cx = vx == vps - 1, cy = vy == vps - 1, cz = vz == vps - 1;
+  int s[8];
+  s[0] = slot;
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+    const bool ux = (c & 4) && cx, uy = (c & 2) && cy, uz = (c & 1) && cz;
+    const int j = (ux ? 4 : 0) | (uy ? 2 : 0) | (uz ? 1 : 0);
+    if (j == c) s[c] = vgx_hash_find(hash, bx + (ux ? 1 : 0), by + (uy ? 1 : 0), bz + (uz ? 1 : 0));
+    else s[c] = s[j];
+  }
+  float o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int x = (vx + ((c >> 2) & 1)) & (vps - 1), y = (vy + ((c >> 1) & 1)) & (vps - 1),
+              z = (vz + (c & 1)) & (vps - 1);
+    float v = __int_as_float(0x7fc00000);
+    if (s[c] >= 0) {
+      const float2 q = dw[(size_t)s[c] * vpb + x + (y << sh) + (z << (2 * sh))];
+      if (q.y > 1e-6f) v = q.x;
+    }
+    o[c] = v;
+  }
+  float4* dst = reinterpret_cast<float4*>(view + i * 8);
+  dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 __global__ void deinterleave_kernel(const float2* __restrict__ dw, float* __restrict__ d,
@@ -205,18 +237,17 @@ static int alloc_submap(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int 
   s->hash.mask = tsize - 1;
   const size_t nvox = (size_t)s->cap_blocks * s->vox_per_block;
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = cudaMalloc(&s->hash.keys, sizeof(uint64_t) * tsize);
-  if (e == cudaSuccess) e = cudaMalloc(&s->hash.vals, sizeof(int32_t) * tsize);
+  if (e == cudaSuccess) e = cudaMalloc(&s->hash.entries, sizeof(VgxHashEntry) * tsize);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_block_idx, sizeof(int32_t) * 3 * s->cap_blocks);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_dw, sizeof(float2) * nvox);
-  if (e == cudaSuccess && with_view) e = cudaMalloc(&s->d_view, sizeof(float) * nvox);
+  if (e == cudaSuccess && with_view) e = cudaMalloc(&s->d_view, sizeof(float) * 8 * nvox);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, sizeof(int) * 4);
   if (e != cudaSuccess) {
     free_submap(s);
     c->set_error(std::string("submap allocation: ") + cudaGetErrorString(e));
     return e == cudaErrorMemoryAllocation ? VGX_ERR_NOMEM : VGX_ERR_CUDA;
   }
-  hash_clear_kernel<<<(tsize + 255) / 256, 256, 0, c->stream>>>(s->hash.keys, s->hash.vals, tsize);
+  hash_clear_kernel<<<(tsize + 255) / 256, 256, 0, c->stream>>>(s->hash.entries, tsize);
   c->launches++;
   VGX_CUDA(c, cudaMemsetAsync(s->d_counters, 0, sizeof(int) * 4, c->stream));
   c->submaps[id] = s;
@@ -248,9 +279,14 @@ extern "C" int vgx_submap_upload(vgx_ctx* c, uint32_t id, float voxel_size, int 
   VGX_CUDA(c, cudaMemcpyAsync(s->d_counters, &s->n_blocks, sizeof(int), cudaMemcpyHostToDevice,
                               c->stream));
   hash_insert_kernel<<<(n_blocks + 127) / 128, 128, 0, c->stream>>>(s->hash, s->d_block_idx, n_blocks);
-  interleave_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(tmp_d, tmp_w, s->d_dw,
-                                                                             s->d_view, nvox);
-  c->launches += 2;
+  interleave_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(tmp_d, tmp_w, s->d_dw, nvox);
+  {
+    int sh = 0;
+    while ((1 << sh) < vps) sh++;
+    build_view_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(
+        s->d_dw, s->d_block_idx, s->hash, s->d_view, n_blocks, vps, sh);
+  }
+  c->launches += 3;
   VGX_CUDA(c, cudaGetLastError());
   VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // host buffers are the caller's
   return VGX_OK;
@@ -275,10 +311,13 @@ extern "C" int vgx_submap_finish(vgx_ctx* c, uint32_t id) {
   if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_finish: unknown submap");
   VGX_CUDA(c, cudaSetDevice(c->device));
   const size_t nvox = (size_t)s->cap_blocks * s->vox_per_block;
-  if (!s->d_view) VGX_CUDA(c, cudaMalloc(&s->d_view, sizeof(float) * nvox));
+  if (!s->d_view) VGX_CUDA(c, cudaMalloc(&s->d_view, sizeof(float) * 8 * nvox));
   const size_t used = (size_t)s->n_blocks * s->vox_per_block;
   if (used > 0) {
-    build_view_kernel<<<(unsigned)((used + 255) / 256), 256, 0, c->stream>>>(s->d_dw, s->d_view, used);
+    int sh = 0;
+    while ((1 << sh) < s->vps) sh++;
+    build_view_kernel<<<(unsigned)((used + 255) / 256), 256, 0, c->stream>>>(
+        s->d_dw, s->d_block_idx, s->hash, s->d_view, s->n_blocks, s->vps, sh);
     c->launches++;
     VGX_CUDA(c, cudaGetLastError());
   }

@@ -175,17 +175,17 @@ tsdf_allocate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
     const uint64_t key = vgx_pack_key(b0, b1, b2);
     uint32_t h = vgx_hash_index(b0, b1, b2, hash.mask);
     for (;;) {
-      const uint64_t k = *((volatile uint64_t*)(hash.keys + h));
+      const uint64_t k = *((volatile uint64_t*)&hash.entries[h].key);
       if (k == key) break;
       if (k == VGX_EMPTY_KEY) {
-        const unsigned long long prev = atomicCAS((unsigned long long*)(hash.keys + h),
+        const unsigned long long prev = atomicCAS((unsigned long long*)&hash.entries[h].key,
                                                   (unsigned long long)VGX_EMPTY_KEY,
                                                   (unsigned long long)key);
         if (prev == VGX_EMPTY_KEY) {
           const int slot = atomicAdd(counters, 1);
           if (slot < capacity) {
             block_idx[3 * slot] = b0; block_idx[3 * slot + 1] = b1; block_idx[3 * slot + 2] = b2;
-            hash.vals[h] = slot;
+            hash.entries[h].val = slot;
           } else {
             counters[1] = 1;  // overflow: block stays unmapped (vals == -1)
           }

@@ -43,9 +43,15 @@ __host__ __device__ __forceinline__ uint32_t vgx_hash_index(int bx, int by, int 
   return (uint32_t)h & mask;
 }
 
+// One 16-byte entry per table slot so a probe is a single 128-bit load.
+struct __align__(16) VgxHashEntry {
+  uint64_t key;   // VGX_EMPTY_KEY when free
+  int32_t val;    // brick slot (-1 while unmapped)
+  int32_t pad;
+};
+
 struct VgxHash {
-  uint64_t* keys;   // VGX_EMPTY_KEY when free
-  int32_t* vals;    // brick slot
+  VgxHashEntry* entries;
   uint32_t mask;    // table_size - 1
 };
 
@@ -54,8 +60,9 @@ __device__ __forceinline__ int vgx_hash_find(const VgxHash& h, int bx, int by, i
   const uint64_t key = vgx_pack_key(bx, by, bz);
   uint32_t i = vgx_hash_index(bx, by, bz, h.mask);
   for (;;) {
-    const uint64_t k = __ldg(h.keys + i);
-    if (k == key) return __ldg(h.vals + i);
+    const int4 e = __ldg(reinterpret_cast<const int4*>(h.entries + i));
+    const uint64_t k = (uint64_t)(uint32_t)e.x | ((uint64_t)(uint32_t)e.y << 32);
+    if (k == key) return e.z;
     if (k == VGX_EMPTY_KEY) return -1;
     i = (i + 1) & h.mask;
   }
@@ -76,10 +83,13 @@ struct VgxSubmap {
   int cap_blocks = 0;
   int n_blocks = 0;            // host mirror (valid after upload / integrate sync)
   bool finished = false;
-  VgxHash hash{nullptr, nullptr, 0};
+  VgxHash hash{nullptr, 0};
   int32_t* d_block_idx = nullptr;  // cap x 3
   float2* d_dw = nullptr;          // cap x vps^3 (distance, weight)
-  float* d_view = nullptr;         // cap x vps^3: distance where observed, NaN elsewhere
+  // Registration view ("octets"): for every voxel the distances of its 2x2x2 forward
+  // neighbourhood (corner i: x = bit2, y = bit1, z = bit0; apron across bricks baked in),
+  // NaN where the voxel is unobserved or its block missing. One 32-byte sector per point.
+  float* d_view = nullptr;         // cap x vps^3 x 8
   int* d_counters = nullptr;       // [0] = n_blocks (device), [1] = overflow flag
   VgxPoints points[2];
 };
