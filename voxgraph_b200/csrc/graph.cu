@@ -17,7 +17,6 @@
 #include "registration.cuh"
 #include "registration_kernels.h"
 
-#define BLK_STRIDE 80   // 64 (J^T J of the residual block, 8x8) + 8 (J^T r) + 1 (sum r^2) + pad
 #define PACK_HDR 4      // [0] cost, [1..3] reserved
 
 struct LmState {
@@ -50,7 +49,7 @@ struct VgxGraph {
   // derived
   std::vector<int> local;  // global indices of this rank's registration constraints
   std::vector<int> block_nodes;  // E x 2 (host copy)
-  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_blk = 0;
+  int n_local = 0, n_tiles = 0, n_rel_local = 0;
   int E = 0;               // off-diagonal blocks
   int n_free = 0;          // reduced dimension 4 * (non-constant nodes)
   int64_t residuals_local = 0, residuals_global = 0;
@@ -65,7 +64,7 @@ struct VgxGraph {
   double* d_partials = nullptr;
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
-  double* d_blk = nullptr;
+  int* d_counters = nullptr;    // per-constraint finished-tile counters
   int* d_csr_begin = nullptr;   // N + E + 1
   int2* d_csr_items = nullptr;  // (blk, role)
   int* d_block_nodes = nullptr; // E x 2
@@ -84,7 +83,7 @@ struct VgxGraph {
 
 static void free_tables(VgxGraph* g) {
   cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin);
-  cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_blk);
+  cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
   cudaFree(g->d_packed[0]); cudaFree(g->d_packed[1]);
@@ -92,7 +91,7 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_state);
   if (g->h_state) cudaFreeHost(g->h_state);
   g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr;
-  g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_blk = nullptr;
+  g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
   g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
   g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
   g->d_packed[0] = g->d_packed[1] = nullptr;
@@ -125,12 +124,14 @@ __device__ __forceinline__ double normalize_angle(double a) {
   return a - two_pi * floor((a + 3.14159265358979323846) / two_pi);
 }
 
-// RelativePoseCostFunction (inl.h:8-70) with the analytic Jacobians autodiff yields.
-__global__ void rel_blocks_kernel(const VgxRelEdge* __restrict__ edges, const double* __restrict__ x,
-                                  double* __restrict__ blk, int n) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  const VgxRelEdge E = edges[e];
+// RelativePoseCostFunction (inl.h:8-70) with the analytic Jacobians autodiff yields:
+// r (4) and J = [dr/dA | dr/dB] (4 x 8), both already multiplied by sqrt_information.
+struct RelEval {
+  double r[4];
+  double J[4][8];
+};
+
+__device__ __forceinline__ void rel_eval(const VgxRelEdge& E, const double* __restrict__ x, RelEval& o) {
   const double* A = x + 4 * E.a;
   const double* B = x + 4 * E.b;
   const double c = cos(A[3]), s = sin(A[3]);
@@ -143,113 +144,112 @@ __global__ void rel_blocks_kernel(const VgxRelEdge* __restrict__ edges, const do
   const double ja[16] = {-c, -s, 0, -s * dx + c * dy, s, -c, 0, -c * dx - s * dy,
                          0, 0, -1, 0, 0, 0, 0, -1};
   const double jb[16] = {c, s, 0, 0, -s, c, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-  double r[4], J[4][8];
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     double acc = 0;
+#pragma unroll
     for (int k = 0; k < 4; ++k) acc += E.L[4 * i + k] * err[k];
-    r[i] = acc;
+    o.r[i] = acc;
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       double sa = 0, sb = 0;
+#pragma unroll
       for (int k = 0; k < 4; ++k) {
         sa += E.L[4 * i + k] * ja[4 * k + j];
         sb += E.L[4 * i + k] * jb[4 * k + j];
       }
-      J[i][j] = sa;
-      J[i][4 + j] = sb;
+      o.J[i][j] = sa;
+      o.J[i][4 + j] = sb;
     }
-  }
-  double* o = blk + (size_t)e * BLK_STRIDE;
-  for (int a = 0; a < 8; ++a) {
-    for (int b = 0; b < 8; ++b) {
-      double h = 0;
-      for (int i = 0; i < 4; ++i) h += J[i][a] * J[i][b];
-      o[8 * a + b] = h;
-    }
-    double g = 0;
-    for (int i = 0; i < 4; ++i) g += J[i][a] * r[i];
-    o[64 + a] = g;
-  }
-  o[72] = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
-}
-
-// csum (21 sums of j = (jr0..jr3, je3)) -> 8x8 block of the residual block.
-__global__ void reg_expand_kernel(const double* __restrict__ csum, double* __restrict__ blk,
-                                  int n, int zero) {
-  const int c = blockIdx.x;
-  const int t = threadIdx.x;  // 0..79
-  if (c >= n || t >= 73) return;
-  const double* s = csum + (size_t)c * VGX_REG_NSTRIDE;
-  double* o = blk + (size_t)c * BLK_STRIDE;
-  if (zero) { o[t] = 0.0; return; }
-  const int m[8] = {0, 1, 2, 3, 0, 1, 2, 4};
-  const double sg[8] = {1, 1, 1, 1, -1, -1, -1, 1};
-  if (t < 64) {
-    const int a = t >> 3, b = t & 7;
-    int p = m[a], q = m[b];
-    if (p > q) { int tmp = p; p = q; q = tmp; }
-    const int idx = p * 5 - (p * (p - 1)) / 2 + (q - p);
-    o[t] = sg[a] * sg[b] * s[idx];
-  } else if (t < 72) {
-    const int a = t - 64;
-    o[t] = sg[a] * s[15 + m[a]];
-  } else {
-    o[72] = s[20];
   }
 }
 
-// One warp per output block: lanes 0..15 the 4x4 entries, lanes 16..19 the gradient
-// (diagonal blocks only). Items are summed in list order -> bit-reproducible.
-__global__ void assemble_kernel(const double* __restrict__ blk, const int* __restrict__ csr_begin,
-                                const int2* __restrict__ items, double* __restrict__ packed, int N,
-                                int E) {
+// Assembly of the packed normal equations, one warp per output block (N diagonal, E
+// off-diagonal, +1 warp for the cost). Lanes 0..15 own the 4x4 entries, lanes 16..19 the
+// gradient of a diagonal block. Contributions are summed in list order -> bit-reproducible.
+// A registration item reads the constraint's 21 sums (csum) and expands them with
+// je[0..2] == -jr[0..2]; a relative-pose item is evaluated on the fly.
+// item = (source, role): source >= 0 registration constraint, < 0 relative edge -(e+1);
+// role 0: A-A, 1: B-B, 2: rows A / cols B, 3: rows B / cols A.
+__global__ void __launch_bounds__(128)
+assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
+                const double* __restrict__ x, const int* __restrict__ csr_begin,
+                const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
+                int n_rel, int exclude_reg) {
   const int ob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (ob >= N + E) return;
+  if (ob > N + E) return;
+  if (ob == N + E) {
+    // cost = 1/2 sum r^2
+    double a = 0;
+    if (!exclude_reg)
+      for (int c = lane; c < n_reg; c += 32) a += csum[(size_t)c * VGX_REG_NSTRIDE + 20];
+    for (int e = lane; e < n_rel; e += 32) {
+      RelEval R;
+      rel_eval(rel[e], x, R);
+      a += R.r[0] * R.r[0] + R.r[1] * R.r[1] + R.r[2] * R.r[2] + R.r[3] * R.r[3];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) {
+      packed[0] = 0.5 * a;
+      packed[1] = 0; packed[2] = 0; packed[3] = 0;
+    }
+    return;
+  }
   const int i0 = csr_begin[ob], i1 = csr_begin[ob + 1];
-  double acc = 0;
   const bool diag = ob < N;
-  if (lane < 16) {
-    const int r = lane >> 2, cc = lane & 3;
-    for (int i = i0; i < i1; ++i) {
-      const int2 it = items[i];
-      const double* b = blk + (size_t)it.x * BLK_STRIDE;
-      int row, col;
+  const int r4 = (lane >> 2) & 3, c4 = lane & 3;
+  double acc = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int2 it = items[i];
+    // (row, col) of the residual block's 8x8 this lane needs; lanes 16..19: gradient row
+    int row, col;
+    if (lane < 16) {
       switch (it.y) {
-        case 0: row = r; col = cc; break;           // A-A
-        case 1: row = 4 + r; col = 4 + cc; break;   // B-B
-        case 2: row = r; col = 4 + cc; break;       // A rows, B cols
-        default: row = 4 + r; col = cc; break;      // B rows, A cols
+        case 0: row = r4; col = c4; break;
+        case 1: row = 4 + r4; col = 4 + c4; break;
+        case 2: row = r4; col = 4 + c4; break;
+        default: row = 4 + r4; col = c4; break;
       }
-      acc += b[8 * row + col];
+    } else {
+      row = (it.y == 0 ? 0 : 4) + (lane & 3);
+      col = -1;
     }
-    double* out = packed + PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob;
-    out[lane] = acc;
-  } else if (lane < 20 && diag) {
-    const int r = lane - 16;
-    for (int i = i0; i < i1; ++i) {
-      const int2 it = items[i];
-      const double* b = blk + (size_t)it.x * BLK_STRIDE;
-      acc += b[64 + (it.y == 0 ? r : 4 + r)];
+    if (it.x >= 0) {
+      if (exclude_reg) continue;
+      const double sv = (lane < VGX_REG_NSUM) ? csum[(size_t)it.x * VGX_REG_NSTRIDE + lane] : 0.0;
+      // 8-vector j8 = (j0, j1, j2, j3, -j0, -j1, -j2, j4): map component a -> (m, sign)
+      const int ma = (row < 4) ? row : (row == 7 ? 4 : row - 4);
+      const double sa = (row >= 4 && row < 7) ? -1.0 : 1.0;
+      int idx;
+      double sgn = sa;
+      if (col >= 0) {
+        const int mb = (col < 4) ? col : (col == 7 ? 4 : col - 4);
+        sgn *= (col >= 4 && col < 7) ? -1.0 : 1.0;
+        const int p = min(ma, mb), q = max(ma, mb);
+        idx = p * 5 - (p * (p - 1)) / 2 + (q - p);
+      } else {
+        idx = 15 + ma;
+      }
+      const double v = __shfl_sync(0xffffffffu, sv, idx);
+      if (lane < 16 || (diag && lane < 20)) acc += sgn * v;
+    } else {
+      RelEval R;
+      rel_eval(rel[-it.x - 1], x, R);
+      double v = 0;
+      if (col >= 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.J[k][col];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.r[k];
+      }
+      if (lane < 16 || (diag && lane < 20)) acc += v;
     }
-    packed[PACK_HDR + 4 * (size_t)ob + r] = acc;
   }
-}
-
-// cost = 1/2 sum over blocks of sum r^2, fixed-order tree.
-__global__ void cost_kernel(const double* __restrict__ blk, int n_blk, double* __restrict__ packed) {
-  __shared__ double s[256];
-  double a = 0;
-  for (int i = threadIdx.x; i < n_blk; i += 256) a += blk[(size_t)i * BLK_STRIDE + 72];
-  s[threadIdx.x] = a;
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    packed[0] = 0.5 * s[0];
-    packed[1] = 0; packed[2] = 0; packed[3] = 0;
-  }
+  if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = acc;
+  else if (lane < 20 && diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = acc;
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -677,7 +677,6 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   g->n_local = (int)cons.size();
   g->n_tiles = (int)tiles.size();
   g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
-  g->n_blk = g->n_rel_local + g->n_local;
 
   // ---- off-diagonal block index over ALL edges (identical on every rank)
   std::map<std::pair<int, int>, int> block_of;
@@ -705,8 +704,8 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
     const int ob = N + block_id(a, b);
     lists[ob].push_back(make_int2(blk, a < b ? 2 : 3));
   };
-  for (int e = 0; e < g->n_rel_local; ++e) add_items(e, g->rel[e].a, g->rel[e].b);
-  for (int k = 0; k < g->n_local; ++k) add_items(g->n_rel_local + k, cons[k].ref_node, cons[k].read_node);
+  for (int e = 0; e < g->n_rel_local; ++e) add_items(-(e + 1), g->rel[e].a, g->rel[e].b);
+  for (int k = 0; k < g->n_local; ++k) add_items(k, cons[k].ref_node, cons[k].read_node);
   std::vector<int> csr_begin(N + g->E + 1, 0);
   std::vector<int2> items;
   for (int ob = 0; ob < N + g->E; ++ob) {
@@ -740,7 +739,8 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_poses, sizeof(RegPoseConst) * g->n_local);
   dmalloc((void**)&g->d_partials, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_tiles);
   dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
-  dmalloc((void**)&g->d_blk, sizeof(double) * BLK_STRIDE * (size_t)g->n_blk);
+  dmalloc((void**)&g->d_counters, sizeof(int) * (size_t)g->n_local);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counters, 0, std::max<size_t>(sizeof(int) * (size_t)g->n_local, 4), st);
   dmalloc((void**)&g->d_xc, sizeof(double) * 4 * N);
   dmalloc((void**)&g->d_packed[0], sizeof(double) * g->packed_len);
   dmalloc((void**)&g->d_packed[1], sizeof(double) * g->packed_len);
@@ -773,24 +773,16 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     {
       VgxLaunchScope s(c, 0);
-      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->d_partials, jacobian);
-    }
-    {
-      VgxLaunchScope s(c, 5);
-      vgx_launch_reg_finalize(st, g->d_cons, g->d_tile_begin, g->d_partials, g->d_csum, g->n_local);
+      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->d_tile_begin,
+                            g->d_counters, g->d_partials, g->d_csum, jacobian);
     }
   }
   {
-    VgxLaunchScope s(c, 5, (g->n_rel_local > 0) + (g->n_local > 0) + 2);
-    if (g->n_rel_local > 0)
-      rel_blocks_kernel<<<(g->n_rel_local + 63) / 64, 64, 0, st>>>(g->d_rel, d_x, g->d_blk, g->n_rel_local);
-    if (g->n_local > 0)
-      reg_expand_kernel<<<g->n_local, 96, 0, st>>>(g->d_csum, g->d_blk + (size_t)g->n_rel_local * BLK_STRIDE,
-                                                   g->n_local, do_reg ? 0 : 1);
-    const int nob = g->N + g->E;
-    assemble_kernel<<<(nob + 3) / 4, 128, 0, st>>>(g->d_blk, g->d_csr_begin, g->d_csr_items, d_packed,
-                                                   g->N, g->E);
-    cost_kernel<<<1, 256, 0, st>>>(g->d_blk, g->n_blk, d_packed);
+    VgxLaunchScope s(c, 5);
+    const int nwarps = g->N + g->E + 1;
+    assemble_kernel<<<(nwarps + 3) / 4, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
+                                                     g->d_csr_items, d_packed, g->N, g->E, g->n_local,
+                                                     g->n_rel_local, do_reg ? 0 : 1);
   }
   VGX_CUDA(c, cudaGetLastError());
   return vgx_nccl_allreduce_sum_f64(c, d_packed, g->packed_len);

@@ -53,7 +53,8 @@ template <bool kJacobian>
 __global__ void __launch_bounds__(VGX_REG_THREADS, 4)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
-                  double* __restrict__ partials) {
+                  const int* __restrict__ tile_begin, int* __restrict__ counters,
+                  double* __restrict__ partials, double* __restrict__ csum) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
   __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
   __shared__ double s_gram[kWarps][64];
@@ -122,21 +123,26 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
     }
     partials[(size_t)blockIdx.x * VGX_REG_NSTRIDE + e] = s;
   }
-}
-
-// Fixed-order sum of the tile partials of each constraint, scaled by factor^2 (cpp:274-291).
-__global__ void reg_finalize_kernel(const RegConstraintDev* __restrict__ constraints,
-                                    const int* __restrict__ tile_begin,
-                                    const double* __restrict__ partials,
-                                    double* __restrict__ csum, int n_constraints) {
-  const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= n_constraints || lane >= VGX_REG_NSUM) return;
-  const int t0 = tile_begin[c], t1 = tile_begin[c + 1];
-  double s = 0;
-  for (int t = t0; t < t1; ++t) s += partials[(size_t)t * VGX_REG_NSTRIDE + lane];
-  const double f = constraints[c].factor;
-  csum[(size_t)c * VGX_REG_NSTRIDE + lane] = s * (f * f);
+  // The last tile of a constraint to finish sums the constraint's partials in tile order
+  // (bit-reproducible) and applies factor^2 (cpp:274-291).
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counters + T.constraint, 1);
+    s_last = (done == t1 - t0 - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < VGX_REG_NSUM) {
+      double s = 0;
+      for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
+      csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (C.factor * C.factor);
+    }
+    if (threadIdx.x == 0) counters[T.constraint] = 0;
+  }
 }
 
 __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ constraints,
@@ -157,20 +163,15 @@ void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, co
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, double* partials, bool jacobian) {
+                           const RegTile* tiles, int n_tiles, const int* tile_begin, int* counters,
+                           double* partials, double* csum, bool jacobian) {
   if (n_tiles <= 0) return;
   if (jacobian)
-    reg_reduce_kernel<true><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, partials);
+    reg_reduce_kernel<true><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, tile_begin,
+                                                                counters, partials, csum);
   else
-    reg_reduce_kernel<false><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, partials);
-}
-
-void vgx_launch_reg_finalize(cudaStream_t st, const RegConstraintDev* cons, const int* tile_begin,
-                             const double* partials, double* csum, int n) {
-  if (n <= 0) return;
-  const int per_block = 4;
-  reg_finalize_kernel<<<(n + per_block - 1) / per_block, 32 * per_block, 0, st>>>(cons, tile_begin,
-                                                                                   partials, csum, n);
+    reg_reduce_kernel<false><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, tile_begin,
+                                                                 counters, partials, csum);
 }
 
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,

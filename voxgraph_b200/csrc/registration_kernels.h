@@ -20,9 +20,9 @@ struct RegTile {
 
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n);
+// Tiles -> partial sums -> (last tile of each constraint) per-constraint sums csum[c][21].
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, double* partials, bool jacobian);
-void vgx_launch_reg_finalize(cudaStream_t st, const RegConstraintDev* cons, const int* tile_begin,
-                             const double* partials, double* csum, int n);
+                           const RegTile* tiles, int n_tiles, const int* tile_begin, int* counters,
+                           double* partials, double* csum, bool jacobian);
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
                         RegConstraintDev* out);
