@@ -102,6 +102,9 @@ typedef struct vgx_tsdf_config {          /* voxblox::TsdfIntegratorBase::Config
   float start_voxel_subsampling_factor;   /* FastTsdfIntegrator, 2 */
   int max_consecutive_ray_collisions;     /* FastTsdfIntegrator, 2 */
   int mode;                               /* 0 simple (every ray, every voxel), 1 fast */
+  int deterministic;                      /* extension, mode 0 only: apply the updates of each voxel
+                                             in ray order (bit-identical to the single-threaded
+                                             reference) instead of lock-free in arrival order */
 } vgx_tsdf_config;
 
 typedef struct vgx_tsdf_stats {
@@ -202,6 +205,9 @@ int vgx_graph_solve(vgx_ctx* ctx, const vgx_solver_options* opts, double* xyzyaw
  * communicator (every rank passes the same full list and holds the submaps it needs);
  * the per-node / per-edge normal-equation blocks are summed with one ncclAllReduce per
  * evaluation. */
+/* Host-only: the constraint -> rank partition the library uses (greedy by descending residual
+ * count, ties to the lowest rank). owner[i] in [0, nranks). */
+int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals, int32_t* owner);
 int vgx_comm_unique_id(uint8_t id[128]);
 int vgx_comm_init(vgx_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
 int vgx_comm_destroy(vgx_ctx* ctx);

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header():
     from voxgraph_b200 import _lib
     # field counts / sizes of the plain-C structs crossing the boundary
-    assert C.sizeof(_lib.TsdfConfig) == 13 * 4
+    assert C.sizeof(_lib.TsdfConfig) == 14 * 4
     assert C.sizeof(_lib.TsdfStats) == 4 * 8
     assert C.sizeof(_lib.RegConfig) == 24
     assert C.sizeof(_lib.SolverOptions) == 8 + 10 * 8 + 8

@@ -1,0 +1,87 @@
+"""N = 2 on real GPUs: pairs sharded over two ranks + one NCCL all-reduce of the packed normal
+equations must reproduce the single-GPU evaluation and solve (skipped with < 2 GPUs)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["VGX_ROOT"])
+from voxgraph_b200 import api, synth
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+sc = synth.make_scene(seed=2, n_submaps=6, n_points=3000, radius=8.0, size_xy=(48.0, 32.0),
+                      n_clutter=80, n_walls=6)
+
+def build(ctx):
+    for s in sc.submaps:
+        ctx.upload_synth_submap(s)
+    pg = api.PoseGraph(ctx)
+    for i in range(len(sc.submaps)):
+        pg.addSubmapNode(api.SubmapNodeConfig(i, sc.poses_init[i], set_constant=(i == 0)))
+    for (i, j, t, y) in sc.odometry:
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(i, j, np.array([*t, y]),
+                                                                      sc.odom_information))
+    for (i, j) in sc.pairs:
+        pg.addRegistrationConstraint(api.RegistrationConstraintConfig(i, j))
+    return pg
+
+single = api.Context(lr)                    # no communicator: evaluates everything
+pg1 = build(single)
+ok, c1, g1, H1 = pg1.evaluate()
+
+multi = api.Context(lr)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid = torch.from_numpy(api.comm_unique_id()).cuda()
+dist.broadcast(uid, 0)
+multi.comm_init(world, rank, uid.cpu().numpy())
+pg2 = build(multi)
+ok, c2, g2, H2 = pg2.evaluate()
+local, glob = multi.graph_num_registration_residuals()
+assert glob == 2 * len(sc.pairs) * 3000 and 0 < local < glob, (local, glob)
+assert abs(c2 - c1) <= 1e-12 * abs(c1), (c1, c2)
+assert np.abs(H2 - H1).max() <= 1e-12 * np.abs(H1).max()
+assert np.abs(g2 - g1).max() <= 1e-12 * np.abs(g1).max()
+# every rank holds the identical all-reduced result
+t = torch.from_numpy(np.concatenate([[c2], g2])).cuda()
+t0 = t.clone(); dist.broadcast(t0, 0)
+assert torch.equal(t, t0)
+opts = dict(parameter_tolerance=1e-7, function_tolerance=1e-12, max_num_iterations=60)
+pg1.solver_options = single.solver_options(**opts); pg2.solver_options = multi.solver_options(**opts)
+s1 = pg1.optimize(); s2 = pg2.optimize()
+x1 = np.array([pg1.getSubmapPoses()[i] for i in range(len(sc.submaps))])
+x2 = np.array([pg2.getSubmapPoses()[i] for i in range(len(sc.submaps))])
+assert np.abs(x1 - x2).max() < 1e-6, np.abs(x1 - x2).max()
+assert s2.final_cost < s2.initial_cost
+xt = torch.from_numpy(x2).cuda(); x0 = xt.clone(); dist.broadcast(x0, 0)
+assert torch.equal(xt, x0)                  # all ranks took the same LM decisions
+print("rank", rank, "multirank ok", local, glob, s2.iterations)
+multi.close(); single.close()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_nccl_allreduce_matches_single(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, VGX_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert p.stdout.count("multirank ok") == 2, p.stdout[-4000:]

@@ -109,6 +109,32 @@ def test_lidar_scan_vs_oracle(ctx, oracle):
         ctx.tsdf_integrate(302, T, pts, gcfg)
 
 
+def test_deterministic_mode_bit_exact_dense_scans(ctx, oracle):
+    """Ray-ordered mode: dense scans (thousands of rays through the same voxels, clearing rays,
+    several scans from different poses) are bit-identical to the single-threaded oracle on every
+    voxel of every block."""
+    world = synth.make_world(3, size_xy=(30.0, 30.0), n_clutter=40, n_walls=4)
+    gcfg, ocfg = _cfg_pair(ctx, oracle)
+    gcfg.deterministic = 1
+    layer = oracle.Layer(VS, 16)
+    ctx.submap_create(310, VS, 16, 4096)
+    tot_g = tot_o = 0
+    for k, (px, py, yaw) in enumerate([(15.0, 15.0, 0.4), (16.5, 14.0, 1.9), (13.0, 16.0, -2.6)]):
+        pts = synth.lidar_scan(world, np.array([px, py, 1.2, yaw]), n_beams=32, n_azimuth=512, seed=k,
+                               miss_range=40.0 if k != 1 else None)
+        T = synth.pose_to_T([px - 15.0, py - 15.0, 0.1 * k, yaw])
+        so = oracle.tsdf_integrate(layer, ocfg, T, pts)
+        sg = ctx.tsdf_integrate(310, T, pts, gcfg)
+        assert (sg.rays_valid, sg.voxel_updates) == (so.rays_valid, so.voxel_updates)
+        tot_g += sg.voxel_updates; tot_o += so.voxel_updates
+    assert tot_g == tot_o > 500000
+    go = _as_dict(*layer.export()); gg = _as_dict(*ctx.submap_download(310))
+    assert set(go) == set(gg)
+    for b in go:
+        assert np.array_equal(go[b][0], gg[b][0]), b
+        assert np.array_equal(go[b][1], gg[b][1]), b
+
+
 def test_fast_mode_properties(ctx, oracle):
     """FastTsdfIntegrator scheduling is race dependent in the reference; check its invariants."""
     world = synth.make_world(3, size_xy=(30.0, 30.0), n_clutter=40, n_walls=4)

@@ -32,7 +32,8 @@ class TsdfConfig(C.Structure):
                 ("sparsity_compensation_factor", C.c_float),
                 ("start_voxel_subsampling_factor", C.c_float),
                 ("max_consecutive_ray_collisions", C.c_int),
-                ("mode", C.c_int)]
+                ("mode", C.c_int),
+                ("deterministic", C.c_int)]
 
 
 class TsdfStats(C.Structure):
@@ -83,7 +84,8 @@ EXPORTS = [
     "vgx_graph_get_poses", "vgx_graph_set_relative_edges",
     "vgx_graph_set_registration_constraints", "vgx_graph_num_registration_residuals",
     "vgx_graph_eval", "vgx_graph_eval_async", "vgx_graph_registration_costs",
-    "vgx_solver_options_default", "vgx_graph_solve", "vgx_comm_unique_id", "vgx_comm_init",
+    "vgx_solver_options_default", "vgx_graph_solve", "vgx_shard_constraints", "vgx_comm_unique_id",
+    "vgx_comm_init",
     "vgx_comm_destroy",
 ]
 
@@ -146,6 +148,7 @@ def load():
     L.vgx_solver_options_default.argtypes = [C.POINTER(SolverOptions)]
     L.vgx_solver_options_default.restype = None
     L.vgx_graph_solve.argtypes = [vp, C.POINTER(SolverOptions), pd, C.POINTER(SolverSummary)]
+    L.vgx_shard_constraints.argtypes = [i32, i32, pi32, pi32]
     L.vgx_comm_unique_id.argtypes = [pu8]
     L.vgx_comm_init.argtypes = [vp, i32, i32, pu8]
     L.vgx_comm_destroy.argtypes = [vp]

@@ -248,6 +248,16 @@ class Context:
         self._check(self._L.vgx_comm_init(self._h, int(nranks), int(rank), _p(u, C.c_uint8)))
 
 
+def shard_constraints(nranks, num_residuals):
+    """Constraint -> rank partition used by the library (host only, no GPU needed)."""
+    cnt = np.ascontiguousarray(num_residuals, np.int32)
+    owner = np.zeros(len(cnt), np.int32)
+    rc = _lib.load().vgx_shard_constraints(int(nranks), len(cnt), _p(cnt, C.c_int32), _p(owner, C.c_int32))
+    if rc != 0:
+        raise VgxError(rc, "vgx_shard_constraints failed")
+    return owner
+
+
 def comm_unique_id():
     u = np.zeros(128, np.uint8)
     rc = _lib.load().vgx_comm_unique_id(_p(u, C.c_uint8))

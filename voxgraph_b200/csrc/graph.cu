@@ -606,6 +606,24 @@ __global__ void lm_init_kernel(const double* __restrict__ packed, const int* __r
   }
 }
 
+// ------------------------------------------------------------------ sharding (host only)
+extern "C" int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals, int32_t* owner) {
+  if (nranks < 1 || n < 0 || (n > 0 && (!num_residuals || !owner))) return VGX_ERR_INVALID;
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return num_residuals[a] > num_residuals[b]; });
+  std::vector<int64_t> load(nranks, 0);
+  for (int i : order) {
+    int best = 0;
+    for (int r = 1; r < nranks; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[i] = best;
+    load[best] += num_residuals[i];
+  }
+  return VGX_OK;
+}
+
 // ------------------------------------------------------------------ table construction
 template <class T>
 static cudaError_t upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t st) {
@@ -639,20 +657,9 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
     if (all[i].n == 0 || all[i].factor == 0.0) g->zero_weight = true;
     g->residuals_global += all[i].n;
   }
-  std::vector<int> owner(P, 0);
-  if (c->nranks > 1) {
-    std::vector<int> order(P);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return all[a].n > all[b].n; });
-    std::vector<int64_t> load(c->nranks, 0);
-    for (int i : order) {
-      int best = 0;
-      for (int r = 1; r < c->nranks; ++r)
-        if (load[r] < load[best]) best = r;
-      owner[i] = best;
-      load[best] += all[i].n;
-    }
-  }
+  std::vector<int32_t> owner(P, 0), counts(P, 0);
+  for (int i = 0; i < P; ++i) counts[i] = all[i].n;
+  vgx_shard_constraints(c->nranks, P, counts.data(), owner.data());
   g->local.clear();
   std::vector<RegConstraintDev> cons;
   std::vector<RegTile> tiles;

@@ -31,6 +31,19 @@ int vgx_ctx::ensure_pinned(size_t bytes) {
   return VGX_OK;
 }
 
+static int grow(vgx_ctx* c, void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return VGX_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = bytes + bytes / 4;
+  VGX_CUDA(c, cudaMalloc(p, want));
+  *cap = want;
+  return VGX_OK;
+}
+int vgx_ctx::ensure_sort(size_t bytes) { return grow(this, &d_sort, &sort_bytes, bytes); }
+int vgx_ctx::ensure_sort2(size_t bytes) { return grow(this, &d_sort2, &sort2_bytes, bytes); }
+
 extern "C" int vgx_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -81,6 +94,8 @@ extern "C" void vgx_ctx_destroy(vgx_ctx* c) {
   vgx_graph_free(c);
   for (auto& kv : c->submaps) free_submap(kv.second);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_sort) cudaFree(c->d_sort);
+  if (c->d_sort2) cudaFree(c->d_sort2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);

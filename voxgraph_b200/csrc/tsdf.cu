@@ -15,6 +15,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cub/cub.cuh>
+
 #include "vgx_internal.h"
 
 #define VGX_EPS 1e-6f
@@ -199,9 +201,11 @@ tsdf_allocate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
 }
 
 // ------------------------------------------------------------------ pass 2: integrate
-__device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const float origin[3],
+// updateTsdfVoxel, part 1: projective sdf (computeDistance) and the update weight
+// (drop-off + sparsity compensation).
+__device__ __forceinline__ void tsdf_update_terms(const TsdfParams& P, const float origin[3],
                                                   const float pG[3], const long long g[3],
-                                                  float weight, float2* voxel) {
+                                                  float weight, float& sdf, float& uw) {
   const float vs = P.voxel_size;
   const float c0 = ((float)g[0] + 0.5f) * vs, c1 = ((float)g[1] + 0.5f) * vs, c2 = ((float)g[2] + 0.5f) * vs;
   const float vv0 = c0 - origin[0], vv1 = c1 - origin[1], vv2 = c2 - origin[2];
@@ -209,8 +213,8 @@ __device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const flo
   const float dist_G = sqrtf(vp0 * vp0 + vp1 * vp1 + vp2 * vp2);
   const float dot = vv0 * vp0 + vv1 * vp1 + vv2 * vp2;
   const float dist_G_V = dot / dist_G;
-  const float sdf = dist_G - dist_G_V;
-  float uw = weight;
+  sdf = dist_G - dist_G_V;
+  uw = weight;
   const float trunc = P.cfg.default_truncation_distance;
   const float dropoff_eps = vs;
   if (P.cfg.use_weight_dropoff && sdf < -dropoff_eps) {
@@ -220,22 +224,115 @@ __device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const flo
   if (P.cfg.use_sparsity_compensation_factor) {
     if (fabsf(sdf) < trunc) uw *= P.cfg.sparsity_compensation_factor;
   }
+}
+
+// updateTsdfVoxel, part 2: the weighted running average with clamping. Returns false when the
+// voxel is left untouched (new_weight < kFloatEpsilon).
+__device__ __forceinline__ bool tsdf_apply(float trunc, float max_weight, float sdf, float uw,
+                                           float& vd, float& vw) {
+  const float new_weight = vw + uw;
+  if (new_weight < VGX_EPS) return false;
+  const float new_sdf = (sdf * uw + vd * vw) / new_weight;
+  vd = (new_sdf > 0.0f) ? fminf(trunc, new_sdf) : fmaxf(-trunc, new_sdf);
+  vw = fminf(max_weight, new_weight);
+  return true;
+}
+
+__device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const float origin[3],
+                                                  const float pG[3], const long long g[3],
+                                                  float weight, float2* voxel) {
+  float sdf, uw;
+  tsdf_update_terms(P, origin, pG, g, weight, sdf, uw);
   unsigned long long* addr = (unsigned long long*)voxel;
   unsigned long long old = *((volatile unsigned long long*)addr);
   for (;;) {
-    const float vd = __uint_as_float((unsigned)(old & 0xffffffffull));
-    const float vw = __uint_as_float((unsigned)(old >> 32));
-    const float new_weight = vw + uw;
-    if (new_weight < VGX_EPS) return;
-    const float new_sdf = (sdf * uw + vd * vw) / new_weight;
-    const float nd = (new_sdf > 0.0f) ? fminf(trunc, new_sdf) : fmaxf(-trunc, new_sdf);
-    const float nw = fminf(P.cfg.max_weight, new_weight);
+    float vd = __uint_as_float((unsigned)(old & 0xffffffffull));
+    float vw = __uint_as_float((unsigned)(old >> 32));
+    if (!tsdf_apply(P.cfg.default_truncation_distance, P.cfg.max_weight, sdf, uw, vd, vw)) return;
     const unsigned long long nv =
-        (unsigned long long)__float_as_uint(nd) | ((unsigned long long)__float_as_uint(nw) << 32);
+        (unsigned long long)__float_as_uint(vd) | ((unsigned long long)__float_as_uint(vw) << 32);
     const unsigned long long prev = atomicCAS(addr, old, nv);
     if (prev == old) return;
     old = prev;
   }
+}
+
+// ------------------------------------------------------------------ deterministic path
+// Ray-ordered integration, bit-identical to the single-threaded reference: every ray emits its
+// (voxel address, sdf, update weight) tuples at a precomputed offset (ray-major), a stable
+// radix sort groups them by voxel keeping ray order, and one thread per voxel applies its
+// updates sequentially.
+__global__ void __launch_bounds__(128)
+tsdf_count_kernel(TsdfParams P, const float* __restrict__ pts, unsigned* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  DevRay rc;
+  float origin[3], pG[3], weight;
+  unsigned c = 0;
+  if (point_to_ray(P, pts, i, rc, origin, pG, weight) && rc.steps >= 0) c = (unsigned)(rc.steps + 1);
+  counts[i] = c;
+}
+
+__global__ void __launch_bounds__(128)
+tsdf_emit_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
+                 const unsigned* __restrict__ offsets, unsigned* __restrict__ keys,
+                 float2* __restrict__ vals, unsigned long long* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_valid = 0, n_upd = 0;
+  if (i < P.n) {
+    DevRay rc;
+    float origin[3], pG[3], weight;
+    if (point_to_ray(P, pts, i, rc, origin, pG, weight)) {
+      n_valid = 1;
+      unsigned o = offsets[i];
+      long long g[3];
+      int lb0 = INT_MIN, lb1 = 0, lb2 = 0, slot = -1;
+      const int vmask = P.vps - 1, sh = P.vps_shift;
+      while (ray_next(rc, g)) {
+        const int b0 = (int)(g[0] >> sh), b1 = (int)(g[1] >> sh), b2 = (int)(g[2] >> sh);
+        if (!(b0 == lb0 && b1 == lb1 && b2 == lb2)) {
+          lb0 = b0; lb1 = b1; lb2 = b2;
+          slot = vgx_hash_find(hash, b0, b1, b2);
+        }
+        unsigned key = 0xFFFFFFFFu;
+        float sdf = 0.f, uw = 0.f;
+        if (slot >= 0) {
+          const int lin = (int)(g[0] & vmask) + (((int)(g[1] & vmask)) << sh) + (((int)(g[2] & vmask)) << (2 * sh));
+          key = ((unsigned)slot << (3 * sh)) + (unsigned)lin;
+          tsdf_update_terms(P, origin, pG, g, weight, sdf, uw);
+          ++n_upd;
+        }
+        keys[o] = key;
+        vals[o] = make_float2(sdf, uw);
+        ++o;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_valid += __shfl_xor_sync(0xffffffffu, n_valid, off);
+    n_upd += __shfl_xor_sync(0xffffffffu, n_upd, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_valid) { atomicAdd(stats + 0, n_valid); atomicAdd(stats + 1, n_valid); }
+    if (n_upd) atomicAdd(stats + 2, n_upd);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tsdf_apply_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ vals, unsigned total,
+                  float2* __restrict__ dw, float trunc, float max_weight) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned key = keys[i];
+  if (key == 0xFFFFFFFFu) return;
+  if (i > 0 && keys[i - 1] == key) return;  // not the head of its voxel's segment
+  float2 v = dw[key];
+  for (unsigned j = i; j < total && keys[j] == key; ++j) {
+    const float2 u = vals[j];
+    tsdf_apply(trunc, max_weight, u.x, u.y, v.x, v.y);
+  }
+  dw[key] = v;
 }
 
 __global__ void __launch_bounds__(128)
@@ -310,6 +407,7 @@ extern "C" void vgx_tsdf_config_default(vgx_tsdf_config* c) {
   c->start_voxel_subsampling_factor = 2.0f;
   c->max_consecutive_ray_collisions = 2;
   c->mode = 0;
+  c->deterministic = 0;
 }
 
 extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7], int n,
@@ -364,7 +462,56 @@ extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7],
     tsdf_allocate_kernel<<<grid, 128, 0, stream>>>(Pa, d_pts, s->hash, s->d_block_idx, s->d_counters,
                                                   s->cap_blocks);
   }
-  {
+  if (P.cfg.mode == 0 && P.cfg.deterministic) {
+    // ---- ray-ordered path: count -> scan -> emit -> stable sort by voxel -> sequential apply
+    const size_t cnt_bytes = ((sizeof(unsigned) * ((size_t)n + 1)) + 255) & ~(size_t)255;
+    size_t scan_tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned*)nullptr, (unsigned*)nullptr, n + 1, stream);
+    rc = c->ensure_sort(2 * cnt_bytes + scan_tmp + 256);
+    if (rc != VGX_OK) return rc;
+    unsigned* d_counts = (unsigned*)c->d_sort;
+    unsigned* d_offsets = (unsigned*)((char*)c->d_sort + cnt_bytes);
+    void* d_scan_tmp = (char*)c->d_sort + 2 * cnt_bytes;
+    unsigned total = 0;
+    {
+      VgxLaunchScope scope(c, 2, 2);
+      VGX_CUDA(c, cudaMemsetAsync(d_counts, 0, cnt_bytes, stream));
+      tsdf_count_kernel<<<grid, 128, 0, stream>>>(P, d_pts, d_counts);
+      cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp, d_counts, d_offsets, n + 1, stream);
+    }
+    VGX_CUDA(c, cudaMemcpyAsync(&total, d_offsets + n, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    VGX_CUDA(c, cudaStreamSynchronize(stream));
+    if (total > 0) {
+      // offsets live in d_sort; the tuple buffers go to d_scratch behind the points
+      const size_t key_bytes = ((sizeof(unsigned) * (size_t)total) + 255) & ~(size_t)255;
+      const size_t val_bytes = ((sizeof(float2) * (size_t)total) + 255) & ~(size_t)255;
+      int end_bit = 3 * P.vps_shift;
+      while ((1u << (end_bit - 3 * P.vps_shift)) < (unsigned)s->cap_blocks) end_bit++;
+      end_bit = end_bit + 1 > 32 ? 32 : end_bit + 1;   // keep the 0xFFFFFFFF sentinel ordered last
+      size_t sort_tmp = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned*)nullptr, (unsigned*)nullptr,
+                                      (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                      (int)total, 0, 32, stream);
+      rc = c->ensure_sort2(2 * key_bytes + 2 * val_bytes + sort_tmp + 256);
+      if (rc != VGX_OK) return rc;
+      char* b2 = (char*)c->d_sort2;
+      unsigned* k_in = (unsigned*)b2;
+      unsigned* k_out = (unsigned*)(b2 + key_bytes);
+      float2* v_in = (float2*)(b2 + 2 * key_bytes);
+      float2* v_out = (float2*)(b2 + 2 * key_bytes + val_bytes);
+      void* d_sort_tmp = b2 + 2 * key_bytes + 2 * val_bytes;
+      (void)end_bit;
+      {
+        VgxLaunchScope scope(c, 2, 3);
+        tsdf_emit_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, d_offsets, k_in, v_in, d_stats);
+        cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_tmp, k_in, k_out, (unsigned long long*)v_in,
+                                        (unsigned long long*)v_out, (int)total, 0, 32, stream);
+        tsdf_apply_kernel<<<(total + 255) / 256, 256, 0, stream>>>(k_out, v_out, total, s->d_dw,
+                                                                   P.cfg.default_truncation_distance,
+                                                                   P.cfg.max_weight);
+      }
+    }
+  } else {
     VgxLaunchScope scope(c, 2);
     tsdf_integrate_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, s->d_dw, d_stats, d_start, d_obs);
   }

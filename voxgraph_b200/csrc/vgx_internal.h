@@ -123,6 +123,10 @@ struct vgx_ctx {
   size_t scratch_bytes = 0;
   void* h_pinned = nullptr;
   size_t pinned_bytes = 0;
+  void* d_sort = nullptr;    // TSDF deterministic path: counts / offsets / scan temp
+  size_t sort_bytes = 0;
+  void* d_sort2 = nullptr;   // ... tuple buffers + radix-sort temp
+  size_t sort2_bytes = 0;
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -134,6 +138,8 @@ struct vgx_ctx {
   }
   int ensure_scratch(size_t bytes);
   int ensure_pinned(size_t bytes);
+  int ensure_sort(size_t bytes);
+  int ensure_sort2(size_t bytes);
 };
 
 // RAII-less helper to bracket kernel launches for accounting.

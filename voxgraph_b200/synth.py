@@ -264,10 +264,24 @@ def figure8(n, size_xy, margin=16.0):
     return x, y, yaw
 
 
+def compose_pose(p, t_rel, yaw_rel):
+    """4-DoF pose p composed with a relative transform expressed in p's frame."""
+    p = np.asarray(p, np.float64)
+    out = np.empty(4)
+    out[:3] = p[:3] + rot_z(p[3]) @ np.asarray(t_rel, np.float64)
+    y = p[3] + yaw_rel
+    out[3] = y - 2 * np.pi * np.floor((y + np.pi) / (2 * np.pi))
+    return out
+
+
 def make_scene(seed=2, n_submaps=50, n_points=10000, voxel_size=0.2, vps=16, radius=12.0,
                size_xy=(120.0, 80.0), max_pairs=None, pose_noise=(0.2, 0.05, 0.02),
-               n_clutter=400, n_walls=24, trunc=None, trajectory=None):
-    """Config-2 style scene: N submaps along a figure-8 through a cluttered hall."""
+               n_clutter=400, n_walls=24, trunc=None, trajectory=None, drift=None):
+    """Config-2 style scene: N submaps along a figure-8 through a cluttered hall.
+
+    drift=(sigma_xy, sigma_z, sigma_yaw) per odometry step: the initial poses are the integrated
+    noisy odometry (what voxgraph starts from) and the odometry edges are those noisy relative
+    transforms; otherwise independent pose noise with near-exact odometry."""
     rng = np.random.default_rng(seed)
     world = make_world(seed, size_xy=size_xy, n_clutter=n_clutter, n_walls=n_walls)
     if trajectory is None:
@@ -279,11 +293,26 @@ def make_scene(seed=2, n_submaps=50, n_points=10000, voxel_size=0.2, vps=16, rad
     poses_gt[:, 3] = yaw_w - 2 * np.pi * np.floor((yaw_w + np.pi) / (2 * np.pi))
     submaps = [make_submap(world, i, poses_gt[i], voxel_size, vps, radius, n_points=n_points,
                            trunc=trunc) for i in range(n_submaps)]
-    noise = np.concatenate([rng.normal(0, pose_noise[0], (n_submaps, 2)),
-                            rng.normal(0, pose_noise[1], (n_submaps, 1)),
-                            rng.normal(0, pose_noise[2], (n_submaps, 1))], -1)
-    noise[0] = 0
-    poses_init = poses_gt + noise
+    odometry = []
+    if drift is None:
+        noise = np.concatenate([rng.normal(0, pose_noise[0], (n_submaps, 2)),
+                                rng.normal(0, pose_noise[1], (n_submaps, 1)),
+                                rng.normal(0, pose_noise[2], (n_submaps, 1))], -1)
+        noise[0] = 0
+        poses_init = poses_gt + noise
+        for i in range(n_submaps - 1):
+            t_obs, yaw_obs = relative_pose(poses_gt[i], poses_gt[i + 1])
+            t_obs = t_obs + rng.normal(0, 0.05, 3) * np.array([1, 1, 0.1])
+            yaw_obs = yaw_obs + rng.normal(0, 0.005)
+            odometry.append((i, i + 1, t_obs, float(yaw_obs)))
+    else:
+        poses_init = poses_gt.copy()
+        for i in range(n_submaps - 1):
+            t_obs, yaw_obs = relative_pose(poses_gt[i], poses_gt[i + 1])
+            t_obs = t_obs + rng.normal(0, 1.0, 3) * np.array([drift[0], drift[0], drift[1]])
+            yaw_obs = float(yaw_obs + rng.normal(0, drift[2]))
+            odometry.append((i, i + 1, t_obs, yaw_obs))
+            poses_init[i + 1] = compose_pose(poses_init[i], t_obs, yaw_obs)
     pairs = []
     for i in range(n_submaps):
         for j in range(i + 1, n_submaps):
@@ -294,12 +323,6 @@ def make_scene(seed=2, n_submaps=50, n_points=10000, voxel_size=0.2, vps=16, rad
     if max_pairs is not None and len(pairs) > max_pairs:
         sel = np.sort(rng.choice(len(pairs), max_pairs, replace=False))
         pairs = [pairs[k] for k in sel]
-    odometry = []
-    for i in range(n_submaps - 1):
-        t_obs, yaw_obs = relative_pose(poses_gt[i], poses_gt[i + 1])
-        t_obs = t_obs + rng.normal(0, 0.05, 3) * np.array([1, 1, 0.1])
-        yaw_obs = yaw_obs + rng.normal(0, 0.005)
-        odometry.append((i, i + 1, t_obs, float(yaw_obs)))
     info = np.diag([1.0, 1.0, 2500.0, 2500.0])  # voxgraph_mapper.yaml:41-47
     return Scene(world, submaps, poses_gt, poses_init, pairs, odometry, info,
                  meta=dict(seed=seed, n_points=n_points, voxel_size=voxel_size, radius=radius))
