@@ -79,6 +79,7 @@ def test_lidar_scan_vs_oracle(ctx, oracle):
     assert pts.shape[0] == 32 * 512
     T = synth.pose_to_T([0.3, -0.2, 0.1, 0.4])
     gcfg, ocfg = _cfg_pair(ctx, oracle)
+    gcfg.deterministic = 0          # lock-free arrival-order path
     layer = oracle.Layer(VS, 16)
     so = oracle.tsdf_integrate(layer, ocfg, T, pts)
     ctx.submap_create(302, VS, 16, 4096)

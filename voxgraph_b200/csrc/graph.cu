@@ -49,7 +49,7 @@ struct VgxGraph {
   // derived
   std::vector<int> local;  // global indices of this rank's registration constraints
   std::vector<int> block_nodes;  // E x 2 (host copy)
-  int n_local = 0, n_tiles = 0, n_rel_local = 0;
+  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_ctas = 0, grid_capacity = 0;
   int E = 0;               // off-diagonal blocks
   int n_free = 0;          // reduced dimension 4 * (non-constant nodes)
   int64_t residuals_local = 0, residuals_global = 0;
@@ -61,6 +61,7 @@ struct VgxGraph {
   RegPoseConst* d_poses = nullptr;
   RegTile* d_tiles = nullptr;
   int* d_tile_begin = nullptr;
+  int* d_cta_tile_begin = nullptr;
   double* d_partials = nullptr;
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
@@ -82,7 +83,7 @@ struct VgxGraph {
 };
 
 static void free_tables(VgxGraph* g) {
-  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin);
+  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_cta_tile_begin);
   cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
@@ -90,7 +91,7 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_A); cudaFree(g->d_scale); cudaFree(g->d_diag); cudaFree(g->d_gs); cudaFree(g->d_step);
   cudaFree(g->d_state);
   if (g->h_state) cudaFreeHost(g->h_state);
-  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr;
+  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_cta_tile_begin = nullptr;
   g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
   g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
   g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
@@ -668,21 +669,44 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   for (int i = 0; i < P; ++i) {
     if (owner[i] != c->rank) continue;
     g->local.push_back(i);
-    tile_begin.push_back((int)tiles.size());
-    for (int s = 0; s < all[i].n; s += VGX_REG_TILE_POINTS) {
-      RegTile t;
-      t.constraint = (int)cons.size();
-      t.start = s;
-      t.count = std::min(VGX_REG_TILE_POINTS, all[i].n - s);
-      t.pad = 0;
-      tiles.push_back(t);
-    }
     cons.push_back(all[i]);
     g->residuals_local += all[i].n;
   }
-  tile_begin.push_back((int)tiles.size());
   g->n_local = (int)cons.size();
+  // Cut the local residual index space evenly over the resident CTAs; a tile is the part of one
+  // CTA's share that lies inside one residual block (so tiles never straddle constraints).
+  const int n_ctas_max = vgx_reg_resident_ctas(c->device);
+  const int64_t R = g->residuals_local;
+  int64_t chunk = (R + n_ctas_max - 1) / std::max(n_ctas_max, 1);
+  chunk = std::max<int64_t>(((chunk + VGX_REG_THREADS - 1) / VGX_REG_THREADS) * VGX_REG_THREADS, VGX_REG_THREADS);
+  g->n_ctas = (int)((R + chunk - 1) / chunk);
+  std::vector<int> cta_tile_begin;
+  {
+    int64_t pos = 0;  // global residual index of the current constraint's first point
+    int next_cta = 0;
+    for (int k = 0; k < g->n_local; ++k) {
+      tile_begin.push_back((int)tiles.size());
+      int s = 0;
+      while (s < cons[k].n) {
+        const int64_t gpos = pos + s;
+        const int cta = (int)(gpos / chunk);
+        const int64_t cta_end = (int64_t)(cta + 1) * chunk;
+        const int cnt = (int)std::min<int64_t>(cons[k].n - s, cta_end - gpos);
+        while (next_cta <= cta) { cta_tile_begin.push_back((int)tiles.size()); ++next_cta; }
+        RegTile t;
+        t.constraint = k; t.start = s; t.count = cnt; t.pad = 0;
+        tiles.push_back(t);
+        s += cnt;
+      }
+      pos += cons[k].n;
+    }
+    while ((int)cta_tile_begin.size() <= g->n_ctas) cta_tile_begin.push_back((int)tiles.size());
+  }
+  tile_begin.push_back((int)tiles.size());
   g->n_tiles = (int)tiles.size();
+  g->grid_capacity = 0;
+  for (const auto& cc : cons)
+    if (cc.grid) g->grid_capacity = std::max(g->grid_capacity, cc.gd0 * cc.gd1 * cc.gd2);
   g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
 
   // ---- off-diagonal block index over ALL edges (identical on every rank)
@@ -734,6 +758,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   if (e == cudaSuccess) e = upload_vec(&g->d_cons, cons, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tiles, tiles, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tile_begin, tile_begin, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_cta_tile_begin, cta_tile_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
@@ -780,8 +805,9 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     {
       VgxLaunchScope s(c, 0);
-      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->d_tile_begin,
-                            g->d_counters, g->d_partials, g->d_csum, jacobian);
+      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_ctas, g->d_cta_tile_begin,
+                            g->d_tile_begin, g->d_counters, g->d_partials, g->d_csum, g->grid_capacity,
+                            jacobian);
     }
   }
   {

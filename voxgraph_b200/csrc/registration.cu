@@ -49,99 +49,144 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 
 #define VGX_STAGE_STRIDE 36  // doubles per component row (32 points + pad: 2-way = optimal for 8 B)
 
+// Persistent CTAs: the residual index space is cut evenly over the grid (148 x resident CTAs per
+// SM); a CTA walks its tiles (a tile never straddles two residual blocks).  Per tile: the
+// reading submap's dense block grid is staged in shared memory, points stream through
+// transform -> voxel index -> grid lookup -> one octet -> residual/Jacobian -> Gram MMA.
 template <bool kJacobian>
-__global__ void __launch_bounds__(VGX_REG_THREADS, 4)
+__global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
-                  const int* __restrict__ tile_begin, int* __restrict__ counters,
-                  double* __restrict__ partials, double* __restrict__ csum) {
+                  const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_begin,
+                  int* __restrict__ counters, double* __restrict__ partials,
+                  double* __restrict__ csum, int grid_capacity) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
   __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
   __shared__ double s_gram[kWarps][64];
-  const RegTile T = tiles[blockIdx.x];
-  const RegConstraintDev C = constraints[T.constraint];
-  const RegPoseConst P = poses[T.constraint];
+  __shared__ int s_last;
+  extern __shared__ int32_t s_grid[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
-  double d0 = 0.0, d1 = 0.0;
+  int grid_of = -1;  // constraint whose block grid is currently staged
 
-  const int end = T.start + T.count;
-  for (int base = T.start; base < end; base += VGX_REG_THREADS) {
-    const int i = base + threadIdx.x;
-    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
-    if (i < end) {
-      const float xi = __ldg(C.px + i), yi = __ldg(C.py + i), zi = __ldg(C.pz + i);
-      const float dist = __ldg(C.pd + i), w = __ldg(C.pw + i);
-      const RegPointResult R = vgx_reg_point<kJacobian>(C, P, xi, yi, zi, dist, w);
-      v5 = R.r;
+  for (int tile = cta_tile_begin[blockIdx.x]; tile < cta_tile_begin[blockIdx.x + 1]; ++tile) {
+    const RegTile T = tiles[tile];
+    const RegConstraintDev C = constraints[T.constraint];
+    const RegPoseConst P = poses[T.constraint];
+    const int cells = C.gd0 * C.gd1 * C.gd2;
+    const bool use_grid = C.grid != nullptr && cells <= grid_capacity;
+    if (use_grid && grid_of != T.constraint) {
+      __syncthreads();  // previous tile's readers are done
+      for (int k = threadIdx.x; k < cells; k += VGX_REG_THREADS) s_grid[k] = __ldg(C.grid + k);
+      grid_of = T.constraint;
+      __syncthreads();
+    }
+    double d0 = 0.0, d1 = 0.0;
+    const int end = T.start + T.count;
+    const size_t vox_shift = 3 * C.vps_shift;
+    for (int base = T.start; base < end; base += VGX_REG_THREADS) {
+      const int i = base + threadIdx.x;
+      const bool act = i < end;
+      const int ic = act ? i : T.start;
+      const float xi = __ldg(C.px + ic), yi = __ldg(C.py + ic), zi = __ldg(C.pz + ic);
+      const float dist = __ldg(C.pd + ic), w = __ldg(C.pw + ic);
+      float p0, p1, p2;
+      vgx_reg_transform(P, xi, yi, zi, p0, p1, p2);
+      RegLocate L;
+      int slot;
+      if (use_grid) {
+        vgx_locate<true>(C, p0, p1, p2, L, s_grid);
+        slot = L.slot;
+      } else {
+        vgx_locate<false>(C, p0, p1, p2, L);
+        slot = vgx_resolve(C, L);
+      }
+      const bool found = slot >= 0;
+      const size_t lin = ((size_t)(found ? slot : 0) << vox_shift) + L.lin;
+      const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
+      const float4 lo = __ldg(o), hi = __ldg(o + 1);
+      const float d[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const bool ok = found && vgx_octet_ok(d);
+      const RegPointResult R = vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, L.ox, L.oy, L.oz);
+      double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+      if (act) {
+        v5 = R.r;
+        if (kJacobian) {
+          v0 = (double)R.jr[0]; v1 = (double)R.jr[1]; v2 = (double)R.jr[2];
+          v3 = (double)R.jr[3]; v4 = (double)R.je3;
+        }
+      }
       if (kJacobian) {
-        v0 = (double)R.jr[0]; v1 = (double)R.jr[1]; v2 = (double)R.jr[2];
-        v3 = (double)R.jr[3]; v4 = (double)R.je3;
+        s_stage[warp][0][lane] = v0; s_stage[warp][1][lane] = v1; s_stage[warp][2][lane] = v2;
+        s_stage[warp][3][lane] = v3; s_stage[warp][4][lane] = v4; s_stage[warp][5][lane] = v5;
+        __syncwarp();
+#pragma unroll
+        for (int t4 = 0; t4 < 8; ++t4) {
+          const double a = (grp < 6) ? s_stage[warp][grp][4 * t4 + tig] : 0.0;
+          dmma_8x8x4(d0, d1, a, a);
+        }
+        __syncwarp();
+      } else {
+        d0 = fma(v5, v5, d0);
       }
     }
+    // ---- tile epilogue: warp Gram fragments -> 21 sums -> partials[tile]
     if (kJacobian) {
-      s_stage[warp][0][lane] = v0; s_stage[warp][1][lane] = v1; s_stage[warp][2][lane] = v2;
-      s_stage[warp][3][lane] = v3; s_stage[warp][4][lane] = v4; s_stage[warp][5][lane] = v5;
-      __syncwarp();
-#pragma unroll
-      for (int t4 = 0; t4 < 8; ++t4) {
-        const double a = (grp < 6) ? s_stage[warp][grp][4 * t4 + tig] : 0.0;
-        dmma_8x8x4(d0, d1, a, a);
-      }
-      __syncwarp();
+      s_gram[warp][grp * 8 + 2 * tig] = d0;
+      s_gram[warp][grp * 8 + 2 * tig + 1] = d1;
     } else {
-      d0 = fma(v5, v5, d0);
-    }
-  }
-  if (kJacobian) {
-    s_gram[warp][grp * 8 + 2 * tig] = d0;
-    s_gram[warp][grp * 8 + 2 * tig + 1] = d1;
-  } else {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, off);
-    if (lane == 0) s_gram[warp][0] = d0;
-  }
-  __syncthreads();
-  if (threadIdx.x < VGX_REG_NSUM) {
-    // entry e of the 21 sums -> (row, col) of the Gram matrix
-    int row = 5, col = 5;
-    const int e = threadIdx.x;
-    if (e < 15) {
-      int p = 0, rem = e;
-      while (rem >= 5 - p) { rem -= 5 - p; ++p; }
-      row = p; col = p + rem;
-    } else if (e < 20) {
-      row = e - 15; col = 5;
+      for (int off = 16; off > 0; off >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, off);
+      if (lane == 0) s_gram[warp][0] = d0;
     }
-    double s = 0;
-    if (kJacobian) {
-#pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][row * 8 + col];
-    } else if (e == 20) {
-#pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
-    }
-    partials[(size_t)blockIdx.x * VGX_REG_NSTRIDE + e] = s;
-  }
-  // The last tile of a constraint to finish sums the constraint's partials in tile order
-  // (bit-reproducible) and applies factor^2 (cpp:274-291).
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
-  if (threadIdx.x == 0) {
-    const int done = atomicAdd(counters + T.constraint, 1);
-    s_last = (done == t1 - t0 - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
+    __syncthreads();
     if (threadIdx.x < VGX_REG_NSUM) {
+      // entry e of the 21 sums -> (row, col) of the Gram matrix
+      int row = 5, col = 5;
+      const int e = threadIdx.x;
+      if (e < 15) {
+        int p = 0, rem = e;
+        while (rem >= 5 - p) { rem -= 5 - p; ++p; }
+        row = p; col = p + rem;
+      } else if (e < 20) {
+        row = e - 15; col = 5;
+      }
       double s = 0;
-      for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
-      csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (C.factor * C.factor);
+      if (kJacobian) {
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][row * 8 + col];
+      } else if (e == 20) {
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
+      }
+      partials[(size_t)tile * VGX_REG_NSTRIDE + e] = s;
     }
-    if (threadIdx.x == 0) counters[T.constraint] = 0;
+    // The last tile of a constraint to finish sums the constraint's partials in tile order
+    // (bit-reproducible) and applies factor^2 (cpp:274-291).
+    const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
+    if (t1 - t0 == 1) {
+      if (threadIdx.x < VGX_REG_NSUM)  // single tile: no ticket needed (same thread wrote the partial)
+        csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] =
+            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (C.factor * C.factor);
+      __syncthreads();
+    } else {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int done = atomicAdd(counters + T.constraint, 1);
+        s_last = (done == t1 - t0 - 1);
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (threadIdx.x < VGX_REG_NSUM) {
+          double s = 0;
+          for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
+          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (C.factor * C.factor);
+        }
+        if (threadIdx.x == 0) counters[T.constraint] = 0;
+      }
+    }
   }
 }
 
@@ -163,15 +208,25 @@ void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, co
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, const int* tile_begin, int* counters,
-                           double* partials, double* csum, bool jacobian) {
-  if (n_tiles <= 0) return;
+                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
+                           const int* tile_begin, int* counters, double* partials, double* csum,
+                           int grid_capacity, bool jacobian) {
+  if (n_ctas <= 0) return;
+  const size_t smem = sizeof(int32_t) * (size_t)grid_capacity;
   if (jacobian)
-    reg_reduce_kernel<true><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, tile_begin,
-                                                                counters, partials, csum);
+    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
+                                                                  tile_begin, counters, partials, csum,
+                                                                  grid_capacity);
   else
-    reg_reduce_kernel<false><<<n_tiles, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, tile_begin,
-                                                                 counters, partials, csum);
+    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
+                                                                   tile_begin, counters, partials, csum,
+                                                                   grid_capacity);
+}
+
+int vgx_reg_resident_ctas(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms * VGX_REG_MIN_BLOCKS;
 }
 
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
@@ -199,6 +254,9 @@ int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx
   C.voxel_size = rd->voxel_size; C.voxel_size_inv = rd->voxel_size_inv;
   C.block_size = rd->block_size; C.block_size_inv = rd->block_size_inv;
   C.vps = rd->vps;
+  C.grid = rd->d_grid;
+  C.gmin0 = rd->grid_min[0]; C.gmin1 = rd->grid_min[1]; C.gmin2 = rd->grid_min[2];
+  C.gd0 = rd->grid_dim[0]; C.gd1 = rd->grid_dim[1]; C.gd2 = rd->grid_dim[2];
   C.vps_shift = 0;
   while ((1 << C.vps_shift) < rd->vps) C.vps_shift++;
   C.factor = (p.sum_w != 0.0) ? (double)p.n / p.sum_w : 0.0;

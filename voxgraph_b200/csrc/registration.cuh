@@ -31,6 +31,8 @@ struct RegConstraintDev {
   const float* view;   // reading octets: 8 floats per voxel, NaN where unobserved / missing
   float voxel_size, voxel_size_inv, block_size, block_size_inv;
   int vps, vps_shift;
+  const int32_t* grid;  // dense block index over the reading submap's block AABB (or null)
+  int gmin0, gmin1, gmin2, gd0, gd1, gd2;
   double factor;       // num_residuals / summed_reference_weight (cpp:274)
   double no_corr;      // config.no_correspondence_cost
 };
@@ -126,14 +128,27 @@ struct RegPointResult {
 // floor(v) as int: single F2I.FLOOR (== (int)floorf(v) for in-range v).
 __device__ __forceinline__ int vgx_floor_idx(float v) { return __float2int_rd(v); }
 
-// getVoxelsAndQVector on the octet view: locate the base corner voxel (the one whose centre
-// is <= pos on every axis, possibly in the lower neighbour block), fetch its 2x2x2 octet with
-// two 128-bit loads. Returns false when the base block is missing or any corner is
-// unobserved / in a missing block (NaN baked into the view).  The reference's first lookup of
-// the block containing pos is implied: that block always holds one of the 8 corners.
-__device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, float p0, float p1,
-                                                  float p2, float d[8], float& ox, float& oy,
-                                                  float& oz) {
+// getVoxelsAndQVector on the octet view, split into phases so that a thread working on several
+// points can keep their loads in flight together:
+//   locate : base corner voxel (the one whose centre is <= pos on every axis, possibly in the
+//            lower neighbour block) + first hash probe issued
+//   resolve: finish the probe sequence -> brick slot
+//   fetch  : the voxel's 2x2x2 octet (two 128-bit loads), NaN test
+// Returns false when the base block is missing or any corner is unobserved / in a missing
+// block (NaN baked into the view).  The reference's first lookup of the block containing pos
+// is implied: that block always holds one of the 8 corners.
+struct RegLocate {
+  float ox, oy, oz;   // q-vector offsets
+  int lin;            // voxel index inside the brick
+  uint32_t h;         // current hash table index
+  uint64_t key;
+  int4 e;             // probed entry
+  int slot;           // kGrid: resolved directly from the shared-memory block grid
+};
+
+template <bool kGrid>
+__device__ __forceinline__ void vgx_locate(const RegConstraintDev& C, float p0, float p1, float p2,
+                                           RegLocate& L, const int32_t* __restrict__ s_grid = nullptr) {
   const int vps = C.vps;
   int b0 = vgx_floor_idx(p0 * C.block_size_inv + VGX_COORD_EPS);
   int b1 = vgx_floor_idx(p1 * C.block_size_inv + VGX_COORD_EPS);
@@ -155,35 +170,66 @@ __device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, flo
   if (p2 - (or2 + ((float)v2 + 0.5f) * C.voxel_size) < 0) {
     if (--v2 < 0) { --b2; v2 += vps; }
   }
-  const int slot = vgx_hash_find(C.hash, b0, b1, b2);
-  if (slot < 0) return false;
+  if (kGrid) {
+    const int g0 = b0 - C.gmin0, g1 = b1 - C.gmin1, g2 = b2 - C.gmin2;
+    const bool in = (unsigned)g0 < (unsigned)C.gd0 && (unsigned)g1 < (unsigned)C.gd1 &&
+                    (unsigned)g2 < (unsigned)C.gd2;
+    L.slot = in ? s_grid[(g2 * C.gd1 + g1) * C.gd0 + g0] : -1;
+  } else {
+    L.key = vgx_pack_key(b0, b1, b2);
+    L.h = vgx_hash_index(b0, b1, b2, C.hash.mask);
+    L.e = __ldg(reinterpret_cast<const int4*>(C.hash.entries + L.h));
+  }
   // q vector offsets from the base corner (block origin recomputed from the moved index)
-  ox = (p0 - ((float)b0 * C.block_size + ((float)v0 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
-  oy = (p1 - ((float)b1 * C.block_size + ((float)v1 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
-  oz = (p2 - ((float)b2 * C.block_size + ((float)v2 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+  L.ox = (p0 - ((float)b0 * C.block_size + ((float)v0 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+  L.oy = (p1 - ((float)b1 * C.block_size + ((float)v1 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
+  L.oz = (p2 - ((float)b2 * C.block_size + ((float)v2 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
   const int sh = C.vps_shift;
-  const size_t lin = ((size_t)slot << (3 * sh)) + v0 + (v1 << sh) + (v2 << (2 * sh));
-  const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
-  const float4 lo = __ldg(o), hi = __ldg(o + 1);
-  d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w;
-  d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
+  L.lin = v0 + (v1 << sh) + (v2 << (2 * sh));
+}
+
+__device__ __forceinline__ int vgx_resolve(const RegConstraintDev& C, RegLocate& L) {
+  for (;;) {
+    const uint64_t k = (uint64_t)(uint32_t)L.e.x | ((uint64_t)(uint32_t)L.e.y << 32);
+    if (k == L.key) return L.e.z;
+    if (k == VGX_EMPTY_KEY) return -1;
+    L.h = (L.h + 1) & C.hash.mask;
+    L.e = __ldg(reinterpret_cast<const int4*>(C.hash.entries + L.h));
+  }
+}
+
+__device__ __forceinline__ bool vgx_octet_ok(const float d[8]) {
   // isObservedVoxel failed / block missing <=> NaN in the octet: the sum is NaN iff any is
   const float chk = ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
   return chk == chk || !(isnan(d[0]) || isnan(d[1]) || isnan(d[2]) || isnan(d[3]) || isnan(d[4]) ||
                          isnan(d[5]) || isnan(d[6]) || isnan(d[7]));
 }
 
+__device__ __forceinline__ bool vgx_interp_gather(const RegConstraintDev& C, float p0, float p1,
+                                                  float p2, float d[8], float& ox, float& oy,
+                                                  float& oz) {
+  RegLocate L;
+  vgx_locate<false>(C, p0, p1, p2, L);
+  const int slot = vgx_resolve(C, L);
+  if (slot < 0) return false;
+  ox = L.ox; oy = L.oy; oz = L.oz;
+  const size_t lin = ((size_t)slot << (3 * C.vps_shift)) + L.lin;
+  const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
+  const float4 lo = __ldg(o), hi = __ldg(o + 1);
+  d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w;
+  d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
+  return vgx_octet_ok(d);
+}
+
+// Everything after the gather: B1 coefficients, interpolation, residual, Jacobian.
 template <bool kJacobian>
-__device__ __forceinline__ RegPointResult vgx_reg_point(const RegConstraintDev& C,
-                                                        const RegPoseConst& P, float xi, float yi,
-                                                        float zi, float dist, float w) {
+__device__ __forceinline__ RegPointResult vgx_reg_math(const RegConstraintDev& C,
+                                                       const RegPoseConst& P, float xi, float yi,
+                                                       float dist, float w, bool ok,
+                                                       const float d[8], float ox, float oy,
+                                                       float oz) {
   RegPointResult R;
-  // cpp:128-129  reading_coordinate = T_reading__reference * reference_coordinate
-  float r0, r1, r2;
-  vgx_rotate_yaw(P.qw, P.qz, xi, yi, zi, r0, r1, r2);
-  const float p0 = r0 + P.tx, p1 = r1 + P.ty, p2 = r2 + P.tz;
-  float d[8], ox = 0, oy = 0, oz = 0;
-  R.ok = vgx_interp_gather(C, p0, p1, p2, d, ox, oy, oz);
+  R.ok = ok;
   R.jr[0] = R.jr[1] = R.jr[2] = R.jr[3] = 0.f;
   R.je3 = 0.f;
   if (!R.ok) {
@@ -239,5 +285,24 @@ __device__ __forceinline__ RegPointResult vgx_reg_point(const RegConstraintDev& 
     R.je3 = m0 * ae03 + m1 * ae13;
   }
   return R;
+}
+
+// cpp:128-129  reading_coordinate = T_reading__reference * reference_coordinate
+__device__ __forceinline__ void vgx_reg_transform(const RegPoseConst& P, float xi, float yi, float zi,
+                                                  float& p0, float& p1, float& p2) {
+  float r0, r1, r2;
+  vgx_rotate_yaw(P.qw, P.qz, xi, yi, zi, r0, r1, r2);
+  p0 = r0 + P.tx; p1 = r1 + P.ty; p2 = r2 + P.tz;
+}
+
+template <bool kJacobian>
+__device__ __forceinline__ RegPointResult vgx_reg_point(const RegConstraintDev& C,
+                                                        const RegPoseConst& P, float xi, float yi,
+                                                        float zi, float dist, float w) {
+  float p0, p1, p2;
+  vgx_reg_transform(P, xi, yi, zi, p0, p1, p2);
+  float d[8], ox = 0, oy = 0, oz = 0;
+  const bool ok = vgx_interp_gather(C, p0, p1, p2, d, ox, oy, oz);
+  return vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, ox, oy, oz);
 }
 #endif  // __CUDACC__

@@ -7,7 +7,9 @@ struct RegConstraintDev;
 struct RegPoseConst;
 
 #define VGX_REG_THREADS 256
-#define VGX_REG_TILE_POINTS 2048   // points per CTA (8 per thread)
+#ifndef VGX_REG_MIN_BLOCKS
+#define VGX_REG_MIN_BLOCKS 4       // resident CTAs per SM the register budget is sized for
+#endif
 #define VGX_REG_NSUM 21            // 15 (upper 5x5) + 5 (gradient) + 1 (cost)
 #define VGX_REG_NSTRIDE 24
 
@@ -20,9 +22,12 @@ struct RegTile {
 
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n);
-// Tiles -> partial sums -> (last tile of each constraint) per-constraint sums csum[c][21].
+// Persistent CTAs walk their tiles -> partial sums -> (last tile of each constraint)
+// per-constraint sums csum[c][21].
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, const int* tile_begin, int* counters,
-                           double* partials, double* csum, bool jacobian);
+                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
+                           const int* tile_begin, int* counters, double* partials, double* csum,
+                           int grid_capacity, bool jacobian);
+int vgx_reg_resident_ctas(int device);
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
                         RegConstraintDev* out);

@@ -4,7 +4,11 @@
 #include <math.h>
 #include <string.h>
 
+#include <limits.h>
+
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "vgx_internal.h"
 
@@ -81,6 +85,7 @@ static void free_submap(VgxSubmap* s) {
   cudaFree(s->d_dw);
   cudaFree(s->d_view);
   cudaFree(s->d_counters);
+  cudaFree(s->d_grid);
   free_points(s->points[0]);
   free_points(s->points[1]);
   delete s;
@@ -218,6 +223,38 @@ __global__ void deinterleave_kernel(const float2* __restrict__ dw, float* __rest
   w[i] = v.y;
 }
 
+// Dense block index over the blocks' AABB (host-built: off the hot path, once per finished submap).
+#define VGX_GRID_MAX_CELLS 4096
+int vgx_submap_build_grid(vgx_ctx* c, VgxSubmap* s) {
+  cudaFree(s->d_grid);
+  s->d_grid = nullptr;
+  s->grid_dim[0] = s->grid_dim[1] = s->grid_dim[2] = 0;
+  const int n = s->n_blocks;
+  if (n <= 0) return VGX_OK;
+  std::vector<int32_t> idx(3 * (size_t)n);
+  VGX_CUDA(c, cudaMemcpyAsync(idx.data(), s->d_block_idx, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost,
+                              c->stream));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], idx[3 * i + a]);
+      hi[a] = std::max(hi[a], idx[3 * i + a]);
+    }
+  const long long cells = (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+  if (cells > VGX_GRID_MAX_CELLS) return VGX_OK;  // sparse / huge: registration uses the hash
+  std::vector<int32_t> grid((size_t)cells, -1);
+  const int dx = hi[0] - lo[0] + 1, dy = hi[1] - lo[1] + 1;
+  for (int i = 0; i < n; ++i)
+    grid[(size_t)(idx[3 * i + 2] - lo[2]) * dy * dx + (size_t)(idx[3 * i + 1] - lo[1]) * dx +
+         (idx[3 * i] - lo[0])] = i;
+  VGX_CUDA(c, cudaMalloc(&s->d_grid, sizeof(int32_t) * cells));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_grid, grid.data(), sizeof(int32_t) * cells, cudaMemcpyHostToDevice, c->stream));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int a = 0; a < 3; ++a) { s->grid_min[a] = lo[a]; s->grid_dim[a] = hi[a] - lo[a] + 1; }
+  return VGX_OK;
+}
+
 // ------------------------------------------------------------------ submap management
 static uint32_t table_size_for(int cap) {
   uint32_t t = 64;
@@ -304,7 +341,7 @@ extern "C" int vgx_submap_upload(vgx_ctx* c, uint32_t id, float voxel_size, int 
   c->launches += 3;
   VGX_CUDA(c, cudaGetLastError());
   VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // host buffers are the caller's
-  return VGX_OK;
+  return vgx_submap_build_grid(c, s);
 }
 
 extern "C" int vgx_submap_create(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int capacity) {
@@ -338,7 +375,7 @@ extern "C" int vgx_submap_finish(vgx_ctx* c, uint32_t id) {
   }
   s->finished = true;
   vgx_graph_invalidate_registration(c);
-  return VGX_OK;
+  return vgx_submap_build_grid(c, s);
 }
 
 extern "C" int vgx_submap_free(vgx_ctx* c, uint32_t id) {

@@ -275,7 +275,7 @@ tsdf_count_kernel(TsdfParams P, const float* __restrict__ pts, unsigned* __restr
 
 __global__ void __launch_bounds__(128)
 tsdf_emit_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
-                 const unsigned* __restrict__ offsets, unsigned* __restrict__ keys,
+                 const unsigned* __restrict__ offsets, unsigned sentinel, unsigned* __restrict__ keys,
                  float2* __restrict__ vals, unsigned long long* __restrict__ stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_valid = 0, n_upd = 0;
@@ -294,7 +294,7 @@ tsdf_emit_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
           lb0 = b0; lb1 = b1; lb2 = b2;
           slot = vgx_hash_find(hash, b0, b1, b2);
         }
-        unsigned key = 0xFFFFFFFFu;
+        unsigned key = sentinel;
         float sdf = 0.f, uw = 0.f;
         if (slot >= 0) {
           const int lin = (int)(g[0] & vmask) + (((int)(g[1] & vmask)) << sh) + (((int)(g[2] & vmask)) << (2 * sh));
@@ -319,20 +319,59 @@ tsdf_emit_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
   }
 }
 
+// Segment heads apply their voxel's updates in order. Short segments (the vast majority) are
+// handled by the head's thread; long ones (voxels near the sensor collect one update per ray)
+// are queued for the warp-cooperative kernel below.
+#define VGX_TSDF_LONG_SEGMENT 64
 __global__ void __launch_bounds__(256)
 tsdf_apply_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ vals, unsigned total,
-                  float2* __restrict__ dw, float trunc, float max_weight) {
+                  unsigned sentinel, float2* __restrict__ dw, float trunc, float max_weight,
+                  unsigned* __restrict__ long_heads, unsigned* __restrict__ n_long) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const unsigned key = keys[i];
-  if (key == 0xFFFFFFFFu) return;
+  if (key >= sentinel) return;
   if (i > 0 && keys[i - 1] == key) return;  // not the head of its voxel's segment
+  // short segment? (bounded look-ahead keeps the loads independent of the recurrence)
+  const unsigned probe = i + VGX_TSDF_LONG_SEGMENT;
+  if (probe < total && keys[probe] == key) {
+    long_heads[atomicAdd(n_long, 1u)] = i;
+    return;
+  }
   float2 v = dw[key];
   for (unsigned j = i; j < total && keys[j] == key; ++j) {
     const float2 u = vals[j];
     tsdf_apply(trunc, max_weight, u.x, u.y, v.x, v.y);
   }
   dw[key] = v;
+}
+
+// One warp per long segment: lanes fetch 32 consecutive tuples (coalesced), then every lane
+// replays them in order through shuffles, so the serial chain is pure ALU latency.
+__global__ void __launch_bounds__(128)
+tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ vals,
+                       unsigned total, float2* __restrict__ dw, float trunc, float max_weight,
+                       const unsigned* __restrict__ long_heads, const unsigned* __restrict__ n_long) {
+  const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (w >= *n_long) return;
+  const unsigned head = long_heads[w];
+  const unsigned key = keys[head];
+  float2 v = dw[key];
+  for (unsigned base = head; base < total; base += 32) {
+    const unsigned j = base + lane;
+    const bool mine = j < total && keys[j] == key;
+    const float2 u = mine ? vals[j] : make_float2(0.f, 0.f);
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    const int cnt = __popc(m);  // the matching lanes form a prefix (keys are sorted)
+    for (int k = 0; k < cnt; ++k) {
+      const float sx = __shfl_sync(0xffffffffu, u.x, k);
+      const float sy = __shfl_sync(0xffffffffu, u.y, k);
+      tsdf_apply(trunc, max_weight, sx, sy, v.x, v.y);
+    }
+    if (cnt < 32) break;
+  }
+  if (lane == 0) dw[key] = v;
 }
 
 __global__ void __launch_bounds__(128)
@@ -407,7 +446,7 @@ extern "C" void vgx_tsdf_config_default(vgx_tsdf_config* c) {
   c->start_voxel_subsampling_factor = 2.0f;
   c->max_consecutive_ray_collisions = 2;
   c->mode = 0;
-  c->deterministic = 0;
+  c->deterministic = 1;  // mode 0 applies updates in ray order by default
 }
 
 extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7], int n,
@@ -485,30 +524,41 @@ extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7],
       // offsets live in d_sort; the tuple buffers go to d_scratch behind the points
       const size_t key_bytes = ((sizeof(unsigned) * (size_t)total) + 255) & ~(size_t)255;
       const size_t val_bytes = ((sizeof(float2) * (size_t)total) + 255) & ~(size_t)255;
-      int end_bit = 3 * P.vps_shift;
-      while ((1u << (end_bit - 3 * P.vps_shift)) < (unsigned)s->cap_blocks) end_bit++;
-      end_bit = end_bit + 1 > 32 ? 32 : end_bit + 1;   // keep the 0xFFFFFFFF sentinel ordered last
+      // keys = slot * 4096 + voxel; the sentinel (unmapped block) is one past the largest key
+      const unsigned long long sent64 = (unsigned long long)s->cap_blocks << (3 * P.vps_shift);
+      if (sent64 >= 0xFFFFFFFFull) VGX_FAIL(c, VGX_ERR_CAPACITY, "submap too large for 32-bit voxel keys");
+      const unsigned sentinel = (unsigned)sent64;
+      int end_bit = 1;
+      while (end_bit < 32 && (1ull << end_bit) <= sent64) end_bit++;
       size_t sort_tmp = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned*)nullptr, (unsigned*)nullptr,
                                       (unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                      (int)total, 0, 32, stream);
-      rc = c->ensure_sort2(2 * key_bytes + 2 * val_bytes + sort_tmp + 256);
+                                      (int)total, 0, end_bit, stream);
+      const size_t heads_bytes = ((sizeof(unsigned) * ((size_t)total / VGX_TSDF_LONG_SEGMENT + 2)) + 255) & ~(size_t)255;
+      rc = c->ensure_sort2(2 * key_bytes + 2 * val_bytes + sort_tmp + heads_bytes + 1024);
       if (rc != VGX_OK) return rc;
       char* b2 = (char*)c->d_sort2;
       unsigned* k_in = (unsigned*)b2;
       unsigned* k_out = (unsigned*)(b2 + key_bytes);
       float2* v_in = (float2*)(b2 + 2 * key_bytes);
       float2* v_out = (float2*)(b2 + 2 * key_bytes + val_bytes);
-      void* d_sort_tmp = b2 + 2 * key_bytes + 2 * val_bytes;
-      (void)end_bit;
+      unsigned* d_nlong = (unsigned*)(b2 + 2 * key_bytes + 2 * val_bytes);
+      unsigned* d_heads = d_nlong + 64;
+      void* d_sort_tmp = b2 + 2 * key_bytes + 2 * val_bytes + 256 + heads_bytes;
       {
-        VgxLaunchScope scope(c, 2, 3);
-        tsdf_emit_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, d_offsets, k_in, v_in, d_stats);
+        VgxLaunchScope scope(c, 2, 4);
+        VGX_CUDA(c, cudaMemsetAsync(d_nlong, 0, 256, stream));
+        tsdf_emit_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, d_offsets, sentinel, k_in, v_in, d_stats);
         cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_tmp, k_in, k_out, (unsigned long long*)v_in,
-                                        (unsigned long long*)v_out, (int)total, 0, 32, stream);
-        tsdf_apply_kernel<<<(total + 255) / 256, 256, 0, stream>>>(k_out, v_out, total, s->d_dw,
-                                                                   P.cfg.default_truncation_distance,
-                                                                   P.cfg.max_weight);
+                                        (unsigned long long*)v_out, (int)total, 0, end_bit, stream);
+        tsdf_apply_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+            k_out, v_out, total, sentinel, s->d_dw, P.cfg.default_truncation_distance, P.cfg.max_weight,
+            d_heads, d_nlong);
+        // at most total / 64 long segments; launch enough warps, the surplus exits
+        const unsigned max_long = total / VGX_TSDF_LONG_SEGMENT + 1;
+        tsdf_apply_long_kernel<<<(max_long + 3) / 4, 128, 0, stream>>>(
+            k_out, v_out, total, s->d_dw, P.cfg.default_truncation_distance, P.cfg.max_weight, d_heads,
+            d_nlong);
       }
     }
   } else {

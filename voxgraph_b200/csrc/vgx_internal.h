@@ -91,6 +91,12 @@ struct VgxSubmap {
   // NaN where the voxel is unobserved or its block missing. One 32-byte sector per point.
   float* d_view = nullptr;         // cap x vps^3 x 8
   int* d_counters = nullptr;       // [0] = n_blocks (device), [1] = overflow flag
+  // Dense block index over the AABB of the allocated blocks (finished submaps): slot or -1.
+  // Small enough to be staged in shared memory by the registration kernel; the hash stays
+  // the general structure (integration, view construction, sparse/huge submaps).
+  int32_t* d_grid = nullptr;
+  int grid_min[3] = {0, 0, 0};
+  int grid_dim[3] = {0, 0, 0};
   VgxPoints points[2];
 };
 
@@ -162,6 +168,7 @@ struct VgxLaunchScope {
   }
 };
 
+int vgx_submap_build_grid(vgx_ctx* ctx, VgxSubmap* s);
 void vgx_graph_free(vgx_ctx* ctx);
 void vgx_graph_invalidate_registration(vgx_ctx* ctx);
 
