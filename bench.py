@@ -374,7 +374,14 @@ def run_b200(args):
                          ("tight", dict(parameter_tolerance=1e-6, function_tolerance=1e-9,
                                         max_num_iterations=50, max_solver_time_s=60.0))):
             ms, summ, x = gpu_solve(**kw)
+            # kernel-time split of one more solve (per-kernel events; not used for solve_ms)
+            ctx.graph_set_poses(pinit); ctx.profile_reset(); ctx.profile_enable(True)
+            ctx.graph_solve(n_nodes, ctx.solver_options(**kw))
+            lm_ms, lm_n = ctx.profile_get(4); rk_ms, rk_n = ctx.profile_get(0); ot_ms, _ = ctx.profile_get(5)
+            ctx.profile_enable(False)
             extras["solve"][name] = {
+                "kernel_ms_split": {"lm_cholesky_step_decide": lm_ms, "registration_reduce": rk_ms,
+                                    "pose_setup_assemble": ot_ms},
                 "solve_ms": ms, "lm_iterations": summ.iterations,
                 "successful_steps": summ.num_successful_steps, "residual_evaluations": summ.num_residual_evals,
                 "termination": summ.termination, "initial_cost": summ.initial_cost,

@@ -160,6 +160,45 @@ def test_small_graph_solve_matches_oracle(ctx, oracle, small_scene):
     assert np.abs(xg - xo).max() < 1e-6
 
 
+@pytest.mark.parametrize("n", [9, 40, 200])
+def test_large_relative_pose_graph(ctx, oracle, n):
+    """Dense-solver sizes up to BASELINE configs[3] (200 nodes -> 796 unknowns): chain + random
+    loop closures with noisy measurements; GPU LM == oracle LM (same schedule, same solution)."""
+    from voxgraph_b200 import api
+    rs = np.random.RandomState(n)
+    gt = np.cumsum(np.concatenate([np.zeros((1, 4)), rs.normal(0, 1, (n - 1, 4)) * [2, 2, 0.1, 0.3]]), 0)
+    gt[:, 3] = _wrap(gt[:, 3])
+    info = np.diag([1.0, 1.0, 2500.0, 2500.0])
+    L = oracle.sqrt_information(info)
+    pg = api.PoseGraph(ctx); og = oracle.Graph()
+    for i in range(n):
+        init = gt[i] + (0 if i == 0 else rs.normal(0, 0.2, 4) * [1, 1, 0.1, 0.1])
+        pg.addSubmapNode(api.SubmapNodeConfig(i, init, set_constant=(i == 0)))
+        og.add_node(i, init, constant=(i == 0))
+    edges = [(i, i + 1) for i in range(n - 1)] + [tuple(sorted(rs.choice(n, 2, replace=False))) for _ in range(3 * n)]
+    for (i, j) in edges:
+        if i == j:
+            continue
+        t, y = synth.relative_pose(gt[i], gt[j])
+        t = t + rs.normal(0, 0.02, 3); y = y + rs.normal(0, 0.002)
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(int(i), int(j), np.array([*t, y]), info))
+        og.add_relative(int(i), int(j), t, y, L)
+    ok, cg_, gg, Hg = pg.evaluate()
+    ok, co, go_, Ho = og.eval()
+    np.testing.assert_allclose(cg_, co, rtol=1e-11)
+    np.testing.assert_allclose(Hg, Ho, rtol=1e-9, atol=1e-9 * np.abs(Ho).max())
+    opts = dict(parameter_tolerance=1e-10, function_tolerance=1e-14, max_num_iterations=100)
+    pg.solver_options = ctx.solver_options(**opts)
+    s = pg.optimize()
+    rc, so = og.solve(oracle.solver_options(num_threads=1, **opts))
+    assert rc == 0
+    xg = np.array([pg.getSubmapPoses()[i] for i in range(n)]); xo = og.poses()
+    assert np.abs(xg[:, :3] - xo[:, :3]).max() < 1e-7
+    assert np.abs(_wrap(xg[:, 3] - xo[:, 3])).max() < 1e-7
+    assert abs(s.final_cost - so.final_cost) <= 1e-8 * max(so.final_cost, 1e-9)
+    assert abs(s.iterations - so.iterations) <= 1
+
+
 def test_solver_errors(ctx, oracle):
     from voxgraph_b200 import api
     pg = api.PoseGraph(ctx)

@@ -14,8 +14,12 @@
 #include <new>
 #include <numeric>
 
+#include <cooperative_groups.h>
+
 #include "registration.cuh"
 #include "registration_kernels.h"
+
+namespace cg = cooperative_groups;
 
 #define PACK_HDR 4      // [0] cost, [1..3] reserved
 
@@ -339,6 +343,15 @@ __global__ void lm_persist_kernel(const double* __restrict__ packed, const int* 
   if (threadIdx.x == 0) st->scale_ready = 1;
 }
 
+// 1/sqrt(d) to double precision from the float MUFU seed + Newton (the fp64 sqrt/div
+// routines cost several hundred cycles each on the serial pivot path).
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double r = (double)rsqrtf((float)d);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) r = r * fma(-0.5 * d, r * r, 1.5);
+  return r;
+}
+
 // Blocked right-looking Cholesky of the (n+1) x (n+1) lower-triangular system, one CTA.
 // smem: sD[32][33] diagonal block, sP[(M - 32)][33] panel.
 #define CH_NB 32
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int 
   const int M = n + 1;
   const int tid = threadIdx.x, T = blockDim.x;
   __shared__ int s_fail;
+  __shared__ double sDinv[CH_NB];
   if (tid == 0) s_fail = 0;
   __syncthreads();
   for (int j0 = 0; j0 < n; j0 += CH_NB) {
@@ -366,10 +380,10 @@ __global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int 
       for (int k = 0; k < nb; ++k) {
         double d = sD[k * 33 + k];
         if (!(d > 0.0) || !isfinite(d)) { if (r == 0) s_fail = 1; d = 1.0; }
-        const double sq = sqrt(d);
+        const double rs = fast_rsqrt(d);
         __syncwarp();
-        if (r == k) sD[k * 33 + k] = sq;
-        if (r > k && r < nb) sD[r * 33 + k] /= sq;
+        if (r == k) { sD[k * 33 + k] = d * rs; sDinv[k] = rs; }
+        if (r > k && r < nb) sD[r * 33 + k] *= rs;
         __syncwarp();
         if (r > k && r < nb) {
           const double lrk = sD[r * 33 + k];
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int 
       for (int c = 0; c < nb; ++c) {
         double v = A[(size_t)(j0 + c) * M + r0 + rr];
         for (int k = 0; k < c; ++k) v -= p[k] * sD[c * 33 + k];
-        v /= sD[c * 33 + c];
+        v *= sDinv[c];
         p[c] = v;
         A[(size_t)(j0 + c) * M + r0 + rr] = v;
       }
@@ -423,19 +437,239 @@ __global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int 
   if (tid == 0 && s_fail) st->step_valid = 0;
 }
 
+// Small systems (n <= ~230, i.e. BASELINE configs[0..1]): the whole packed lower triangle of
+// the (n+1) x (n+1) augmented matrix lives in shared memory; one CTA factors it column by
+// column (pivot via fast_rsqrt, warps over trailing columns, lanes over rows), the rhs row
+// gives the forward substitution for free, then the back substitution writes x = (L L^T)^-1 g.
+__device__ __forceinline__ int tri_off(int j, int M) { return j * M - (j * (j - 1)) / 2; }
+
+__device__ __forceinline__ void dmma_sub_8x8x4(double& c0, double& c1, double a, double b) {
+  // C += A * B on the FP64 tensor core (callers negate)
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Left-looking, panel width 8: (1) the block column is updated with all previous columns by
+// m8n8k4 FP64 MMAs (warps over 8-row tiles), (2) warp 0 factors the 8x8 diagonal block,
+// (3) one thread per row solves the panel.  Then back substitution in place.
+#define CS_NB 8
+__global__ void __launch_bounds__(1024)
+chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__ xsol,
+                       LmState* __restrict__ st) {
+  extern __shared__ double S[];  // packed columns: column j holds rows j..n
+  __shared__ int s_fail;
+  const int M = n + 1;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* rinv = S + tri_off(M, M);  // n reciprocals of the diagonal of L
+  if (tid == 0) s_fail = 0;
+  for (int j = warp; j < M; j += nw) {
+    const int o = tri_off(j, M);
+    for (int i = j + lane; i < M; i += 32) S[o + i - j] = A[(size_t)j * M + i];
+  }
+  __syncthreads();
+  for (int J0 = 0; J0 < n; J0 += CS_NB) {
+    const int nb = min(CS_NB, n - J0);
+    // (1) A[J0.., J0..J0+8) -= L[J0.., 0..J0) * L[J0..J0+8, 0..J0)^T
+    if (J0 > 0) {
+      const int ntiles = (M - J0 + 7) >> 3;
+      for (int tile = warp; tile < ntiles; tile += nw) {
+        const int i0 = J0 + 8 * tile;
+        const int ra = i0 + g;        // row of this lane's A fragment element
+        const int rb = J0 + g;        // row (= column of the block) of its B fragment element
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < J0; k0 += 4) {
+          const int kc = k0 + t;      // J0 is a multiple of 8, so kc < J0
+          const int ok = tri_off(kc, M) - kc;
+          const double a = (ra < M) ? S[ok + ra] : 0.0;
+          const double b = (rb < n) ? S[ok + rb] : 0.0;
+          dmma_sub_8x8x4(c0, c1, a, b);
+        }
+        // lane holds C[g][2t], C[g][2t+1] -> element (row i0+g, col J0+2t(+1)), lower part only
+        const int r = i0 + g;
+        if (r < M) {
+          const int cA = J0 + 2 * t, cB = cA + 1;
+          if (cA < n && cA < J0 + nb && r >= cA) S[tri_off(cA, M) + r - cA] -= c0;
+          if (cB < n && cB < J0 + nb && r >= cB) S[tri_off(cB, M) + r - cB] -= c1;
+        }
+      }
+    }
+    __syncthreads();
+    // (2) factor the diagonal block (warp 0; lane = row inside the block)
+    if (warp == 0) {
+      for (int k = 0; k < nb; ++k) {
+        const int ok = tri_off(J0 + k, M);
+        double d = S[ok];
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = 1; d = 1.0; }
+        const double rs = fast_rsqrt(d);
+        __syncwarp();
+        if (lane == k) { S[ok] = d * rs; rinv[J0 + k] = rs; }
+        if (lane > k && lane < nb) S[ok + lane - k] *= rs;
+        __syncwarp();
+        if (lane > k && lane < nb) {
+          const double lrk = S[ok + lane - k];
+          for (int c = k + 1; c <= lane; ++c)
+            S[tri_off(J0 + c, M) + lane - c] -= lrk * S[ok + c - k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // (3) panel solve: rows below the block (incl. the rhs row n)
+    for (int r = J0 + nb + tid; r < M; r += T) {
+      double x[CS_NB];
+#pragma unroll
+      for (int c = 0; c < CS_NB; ++c) {
+        if (c < nb) {
+          const int oc = tri_off(J0 + c, M);
+          double v = S[oc + r - (J0 + c)];
+#pragma unroll
+          for (int k = 0; k < CS_NB; ++k)
+            if (k < c) v -= x[k] * S[tri_off(J0 + k, M) + c - k];
+          v *= rinv[J0 + c];
+          x[c] = v;
+          S[oc + r - (J0 + c)] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution L^T x = y, y = row n of L, kept in place (element n of each column)
+  for (int k = n - 1; k >= 0; --k) {
+    const int ok = tri_off(k, M);
+    if (tid == 0) S[ok + n - k] *= rinv[k];   // x_k
+    __syncthreads();
+    const double xk = S[ok + n - k];
+    for (int i = tid; i < k; i += T) {
+      const int oi = tri_off(i, M);
+      S[oi + n - i] = fma(-S[oi + k - i], xk, S[oi + n - i]);
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < n; k += T) xsol[k] = S[tri_off(k, M) + n - k];
+  if (tid == 0 && s_fail) st->step_valid = 0;
+}
+
+// Multi-CTA variant (cooperative launch, grid-wide barriers): every CTA factors the 32x32
+// diagonal block redundantly in shared memory (deterministic, saves a barrier), the panel rows
+// and the 32x32 trailing tiles are spread over the grid.  Two grid syncs per panel.
+__global__ void __launch_bounds__(256) chol_coop_kernel(double* __restrict__ A, int n,
+                                                        LmState* __restrict__ st) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sD[CH_NB * 33];
+  __shared__ double sPi[CH_NB * 33];
+  __shared__ double sPj[CH_NB * 33];
+  __shared__ double sDinv[CH_NB];
+  __shared__ int s_fail;
+  const int M = n + 1;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int gsize = gridDim.x * T, gid = blockIdx.x * T + tid;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += CH_NB) {
+    const int nb = min(CH_NB, n - j0);
+    for (int t = tid; t < nb * nb; t += T) {
+      const int r = t % nb, c = t / nb;
+      if (r >= c) sD[r * 33 + c] = A[(size_t)(j0 + c) * M + j0 + r];
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int r = tid;
+      for (int k = 0; k < nb; ++k) {
+        double d = sD[k * 33 + k];
+        if (!(d > 0.0) || !isfinite(d)) { if (r == 0) s_fail = 1; d = 1.0; }
+        const double rs = fast_rsqrt(d);
+        __syncwarp();
+        if (r == k) { sD[k * 33 + k] = d * rs; sDinv[k] = rs; }
+        if (r > k && r < nb) sD[r * 33 + k] *= rs;
+        __syncwarp();
+        if (r > k && r < nb) {
+          const double lrk = sD[r * 33 + k];
+          for (int c = k + 1; c <= r; ++c) sD[r * 33 + c] -= lrk * sD[c * 33 + k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+      for (int t = tid; t < nb * nb; t += T) {
+        const int r = t % nb, c = t / nb;
+        if (r >= c) A[(size_t)(j0 + c) * M + j0 + r] = sD[r * 33 + c];
+      }
+    // panel solve: one thread of the grid per row below the block (incl. the rhs row n)
+    const int r0 = j0 + nb;
+    const int rows = M - r0;
+    for (int rr = gid; rr < rows; rr += gsize) {
+      double x[CH_NB];
+#pragma unroll
+      for (int c = 0; c < CH_NB; ++c) {
+        if (c < nb) {
+          double v = A[(size_t)(j0 + c) * M + r0 + rr];
+#pragma unroll
+          for (int k = 0; k < CH_NB; ++k)
+            if (k < c) v -= x[k] * sD[c * 33 + k];
+          v *= sDinv[c];
+          x[c] = v;
+          A[(size_t)(j0 + c) * M + r0 + rr] = v;
+        }
+      }
+    }
+    grid.sync();
+    // trailing update over 32x32 tiles (bi >= bj) of rows/cols [r0, M) x [r0, n)
+    const int tc = n - r0;
+    if (tc > 0) {
+      const int ntr = (rows + CH_NB - 1) / CH_NB;   // tile rows (incl. rhs row)
+      const int ntc = (tc + CH_NB - 1) / CH_NB;     // tile cols
+      for (int tile = blockIdx.x; tile < ntr * ntc; tile += gridDim.x) {
+        const int bi = tile / ntc, bj = tile % ntc;
+        if (bi < bj) continue;
+        __syncthreads();
+        for (int t = tid; t < CH_NB * CH_NB; t += T) {
+          const int r = t % CH_NB, k = t / CH_NB;
+          const int ri = bi * CH_NB + r, rj = bj * CH_NB + r;
+          sPi[r * 33 + k] = (ri < rows) ? A[(size_t)(j0 + k) * M + r0 + ri] : 0.0;
+          sPj[r * 33 + k] = (rj < rows) ? A[(size_t)(j0 + k) * M + r0 + rj] : 0.0;
+        }
+        __syncthreads();
+        // 256 threads x 4 outputs: thread owns column cj = tid / 8, rows (tid % 8) + 8 * q
+        const int cj = tid >> 3, rb = tid & 7;
+        double acc[4] = {0, 0, 0, 0};
+#pragma unroll 8
+        for (int k = 0; k < CH_NB; ++k) {
+          const double pj = sPj[cj * 33 + k];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = fma(sPi[(rb + 8 * q) * 33 + k], pj, acc[q]);
+        }
+        const int gc = bj * CH_NB + cj;
+        if (gc < tc) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gr = bi * CH_NB + rb + 8 * q;
+            if (gr < rows && gr >= gc) A[(size_t)(r0 + gc) * M + r0 + gr] -= acc[q];
+          }
+        }
+      }
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && tid == 0 && s_fail) st->step_valid = 0;
+}
+
 // Back substitution L^T x = y (y = row n of L), step = -x, model cost change, candidate.
 __global__ void __launch_bounds__(1024)
 lm_step_kernel(const double* __restrict__ A, int n, int N, const int* __restrict__ red,
                const double* __restrict__ scale, const double* __restrict__ diag,
                const double* __restrict__ gs, const double* __restrict__ x,
-               double* __restrict__ xc, double* __restrict__ step, LmState* __restrict__ st) {
+               double* __restrict__ xc, double* __restrict__ step, LmState* __restrict__ st,
+               const double* __restrict__ presolved) {
   extern __shared__ double sy[];  // n
   __shared__ double s_red[3][32];
   const int M = n + 1;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-  for (int i = tid; i < n; i += T) sy[i] = A[(size_t)i * M + n];
+  for (int i = tid; i < n; i += T) sy[i] = presolved ? presolved[i] : A[(size_t)i * M + n];
   __syncthreads();
-  const int nblk = (n + CH_NB - 1) / CH_NB;
+  const int nblk = presolved ? 0 : (n + CH_NB - 1) / CH_NB;
   for (int b = nblk - 1; b >= 0; --b) {
     const int j0 = b * CH_NB, nb = min(CH_NB, n - j0);
     // solve the nb x nb upper-triangular block (warp 0)
@@ -1042,10 +1276,30 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
     if (summary) *summary = S;
     VGX_FAIL(c, VGX_ZERO_WEIGHT, "a registration constraint has zero summed weight (Evaluate == false)");
   }
+  // dense Cholesky: whole system in shared memory when it fits (configs[0..1]), else the
+  // cooperative multi-CTA kernel, else one CTA streaming from global memory
+  const size_t smem_chol_bytes = sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + n + 2);
+  const bool use_smem_chol = n > 0 && smem_chol_bytes <= 220 * 1024;
+  if (use_smem_chol)
+    VGX_CUDA(c, cudaFuncSetAttribute(chol_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_chol_bytes));
+  int coop_grid = 0;
+  if (!use_smem_chol) {
+    int coop = 0, sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_coop_kernel, 256, 0) == cudaSuccess &&
+        per_sm > 0) {
+      const int tiles = ((n + 1 + CH_NB - 1) / CH_NB) * ((n + CH_NB - 1) / CH_NB);
+      coop_grid = std::max(1, std::min(sms * std::min(per_sm, 2), std::max(tiles / 2, (n + 256) / 256)));
+    }
+  }
   const size_t chol_smem = sizeof(double) * ((size_t)CH_NB * 33 + (size_t)std::max(n + 1 - CH_NB, 1) * 33);
-  if (chol_smem > 227 * 1024)
-    VGX_FAIL(c, VGX_ERR_CAPACITY, "pose graph too large for the single-CTA dense solver (max ~219 free nodes)");
-  VGX_CUDA(c, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+  if (coop_grid == 0) {
+    if (chol_smem > 227 * 1024)
+      VGX_FAIL(c, VGX_ERR_CAPACITY, "pose graph too large for the single-CTA dense solver (max ~219 free nodes)");
+    VGX_CUDA(c, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+  }
 
   LmOpts lo;
   lo.max_num_iterations = o->max_num_iterations;
@@ -1083,10 +1337,18 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
           g->d_gs, g->d_state, lo);
       lm_persist_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_red_offset, N, g->d_scale, g->d_diag,
                                            g->d_state, lo);
-      chol_kernel<<<1, 1024, chol_smem, st>>>(g->d_A, n, g->d_state);
+      if (use_smem_chol) {
+        chol_solve_smem_kernel<<<1, 1024, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state);
+      } else if (coop_grid > 0) {
+        int n_arg = n;
+        void* args[] = {(void*)&g->d_A, (void*)&n_arg, (void*)&g->d_state};
+        VGX_CUDA(c, cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(coop_grid), dim3(256), args, 0, st));
+      } else {
+        chol_kernel<<<1, 1024, chol_smem, st>>>(g->d_A, n, g->d_state);
+      }
       lm_step_kernel<<<1, 1024, sizeof(double) * n, st>>>(g->d_A, n, N, g->d_red_offset, g->d_scale,
                                                          g->d_diag, g->d_gs, g->d_x, g->d_xc, g->d_step,
-                                                         g->d_state);
+                                                         g->d_state, use_smem_chol ? g->d_step : nullptr);
     }
     VGX_CUDA(c, cudaGetLastError());
     // candidate evaluated with Jacobians so an accepted step needs no second pass
