@@ -169,8 +169,8 @@ __device__ __forceinline__ void rel_eval(const VgxRelEdge& E, const double* __re
   }
 }
 
-// Assembly of the packed normal equations, one warp per output block (N diagonal, E
-// off-diagonal, +1 warp for the cost). Lanes 0..15 own the 4x4 entries, lanes 16..19 the
+// Assembly of the packed normal equations, one 4-warp CTA per output block (N diagonal, E
+// off-diagonal, +1 for the cost). Lanes 0..15 own the 4x4 entries, lanes 16..19 the
 // gradient of a diagonal block. Contributions are summed in list order -> bit-reproducible.
 // A registration item reads the constraint's 21 sums (csum) and expands them with
 // je[0..2] == -jr[0..2]; a relative-pose item is evaluated on the fly.
@@ -181,23 +181,27 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
                 const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
                 int n_rel, int exclude_reg) {
-  const int ob = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (ob > N + E) return;
+  // one CTA (4 warps) per output block: warp w sums items w, w+4, ... ; the four partial sums
+  // are combined in warp order -> bit-reproducible
+  __shared__ double s_part[4][20];
+  const int ob = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ob == N + E) {
     // cost = 1/2 sum r^2
     double a = 0;
     if (!exclude_reg)
-      for (int c = lane; c < n_reg; c += 32) a += csum[(size_t)c * VGX_REG_NSTRIDE + 20];
-    for (int e = lane; e < n_rel; e += 32) {
+      for (int c = threadIdx.x; c < n_reg; c += 128) a += csum[(size_t)c * VGX_REG_NSTRIDE + 20];
+    for (int e = threadIdx.x; e < n_rel; e += 128) {
       RelEval R;
       rel_eval(rel[e], x, R);
       a += R.r[0] * R.r[0] + R.r[1] * R.r[1] + R.r[2] * R.r[2] + R.r[3] * R.r[3];
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if (lane == 0) {
-      packed[0] = 0.5 * a;
+    if (lane == 0) s_part[warp][0] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      packed[0] = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
       packed[1] = 0; packed[2] = 0; packed[3] = 0;
     }
     return;
@@ -206,7 +210,7 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
   const bool diag = ob < N;
   const int r4 = (lane >> 2) & 3, c4 = lane & 3;
   double acc = 0;
-  for (int i = i0; i < i1; ++i) {
+  for (int i = i0 + warp; i < i1; i += 4) {
     const int2 it = items[i];
     // (row, col) of the residual block's 8x8 this lane needs; lanes 16..19: gradient row
     int row, col;
@@ -238,7 +242,7 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
         idx = 15 + ma;
       }
       const double v = __shfl_sync(0xffffffffu, sv, idx);
-      if (lane < 16 || (diag && lane < 20)) acc += sgn * v;
+      acc += sgn * v;
     } else {
       RelEval R;
       rel_eval(rel[-it.x - 1], x, R);
@@ -250,11 +254,16 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.r[k];
       }
-      if (lane < 16 || (diag && lane < 20)) acc += v;
+      acc += v;
     }
   }
-  if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = acc;
-  else if (lane < 20 && diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = acc;
+  if (lane < 20) s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && lane < 20) {
+    const double tot = ((s_part[0][lane] + s_part[1][lane]) + s_part[2][lane]) + s_part[3][lane];
+    if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
+    else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
+  }
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -535,15 +544,32 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
     }
     __syncthreads();
   }
-  // back substitution L^T x = y, y = row n of L, kept in place (element n of each column)
-  for (int k = n - 1; k >= 0; --k) {
-    const int ok = tri_off(k, M);
-    if (tid == 0) S[ok + n - k] *= rinv[k];   // x_k
+  // back substitution L^T x = y (y = row n of L, kept in place as element n of each column),
+  // blocked by 8: warp 0 solves the 8 unknowns of a block, then every thread folds them into
+  // the remaining right-hand side with 8 FMAs.
+  for (int J0 = ((n - 1) / CS_NB) * CS_NB; J0 >= 0; J0 -= CS_NB) {
+    const int nb = min(CS_NB, n - J0);
+    if (warp == 0) {
+      for (int k = nb - 1; k >= 0; --k) {
+        const int ok = tri_off(J0 + k, M);
+        const double xk = S[ok + n - (J0 + k)] * rinv[J0 + k];
+        __syncwarp();
+        if (lane == 0) S[ok + n - (J0 + k)] = xk;
+        if (lane < k) {
+          const int oi = tri_off(J0 + lane, M);
+          S[oi + n - (J0 + lane)] = fma(-S[oi + k - lane], xk, S[oi + n - (J0 + lane)]);
+        }
+        __syncwarp();
+      }
+    }
     __syncthreads();
-    const double xk = S[ok + n - k];
-    for (int i = tid; i < k; i += T) {
+    for (int i = tid; i < J0; i += T) {
       const int oi = tri_off(i, M);
-      S[oi + n - i] = fma(-S[oi + k - i], xk, S[oi + n - i]);
+      double y = S[oi + n - i];
+#pragma unroll
+      for (int k = 0; k < CS_NB; ++k)
+        if (k < nb) y = fma(-S[oi + (J0 + k) - i], S[tri_off(J0 + k, M) + n - (J0 + k)], y);
+      S[oi + n - i] = y;
     }
     __syncthreads();
   }
@@ -1046,8 +1072,7 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   }
   {
     VgxLaunchScope s(c, 5);
-    const int nwarps = g->N + g->E + 1;
-    assemble_kernel<<<(nwarps + 3) / 4, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
+    assemble_kernel<<<g->N + g->E + 1, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
                                                      g->d_csr_items, d_packed, g->N, g->E, g->n_local,
                                                      g->n_rel_local, do_reg ? 0 : 1);
   }
