@@ -243,12 +243,25 @@ def run_b200(args):
     S = len(sc.submaps)
 
     ctx = api.Context(local_rank)
+    comm_kind = None
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.from_numpy(api.comm_unique_id()).cuda()
         dist.broadcast(uid, 0)
         ctx.comm_init(world, rank, uid.cpu().numpy())
+        if os.environ.get("VGX_COMM", "p2p") == "p2p":
+            # NVLink peer-memory exchange of the packed normal equations (CUDA IPC); NCCL stays
+            # initialised as the fallback path (VGX_COMM=nccl selects it)
+            def all_gather_bytes(h):
+                t = torch.from_numpy(h).cuda()
+                out = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(out, t)
+                return out.cpu().numpy()
+            api.p2p_setup(ctx, world, rank, all_gather_bytes, capacity_doubles=1 << 20)
+            comm_kind = "nvlink-p2p one-shot all-gather-reduce (CUDA IPC)"
+        else:
+            comm_kind = "ncclAllReduce"
 
     t_up = time.time()
     bricks_bytes = 0
@@ -467,7 +480,7 @@ def run_b200(args):
                 "clocks": clocks, "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample",
                                                        "value_4_threads", "note")} if cpu else None),
-                "upload_s": upload_s, "resident_bytes": {"points": int(r_global // max(n_gpus, 1) * 20),
+                "collective": comm_kind, "upload_s": upload_s, "resident_bytes": {"points": int(r_global // max(n_gpus, 1) * 20),
                                                          "reading_bricks_view": int(bricks_bytes)}}
         line.update(extras)
         _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()

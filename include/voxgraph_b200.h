@@ -205,12 +205,25 @@ int vgx_graph_solve(vgx_ctx* ctx, const vgx_solver_options* opts, double* xyzyaw
  * communicator (every rank passes the same full list and holds the submaps it needs);
  * the per-node / per-edge normal-equation blocks are summed with one ncclAllReduce per
  * evaluation. */
-/* Host-only: the constraint -> rank partition the library uses (greedy by descending residual
- * count, ties to the lowest rank). owner[i] in [0, nranks). */
-int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals, int32_t* owner);
+/* Host-only: the constraint -> rank partition the library uses. Constraints are ordered by
+ * locality key (the reading submap id; NULL = input order; ties keep input order) and that
+ * sequence is cut into nranks contiguous pieces of equal residual count, so a rank gathers from
+ * few reading submaps (L2 locality) and loads differ by at most one constraint.
+ * owner[i] in [0, nranks). */
+int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals,
+                          const uint32_t* locality_keys, int32_t* owner);
 int vgx_comm_unique_id(uint8_t id[128]);
 int vgx_comm_init(vgx_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
 int vgx_comm_destroy(vgx_ctx* ctx);
+/* NVLink peer-memory exchange (single node, <= 8 ranks): replaces the NCCL all-reduce of the
+ * packed normal equations by a one-shot all-gather-reduce over CUDA-IPC mapped peer buffers:
+ * the assembly kernel writes the rank's partial into its exported buffer, a flag store signals
+ * every peer, and each rank sums all partials in rank order straight out of peer memory
+ * (bit-identical on all ranks). export: allocate + get the 64-byte IPC handle; import: map
+ * the peers (handles = nranks x 64 bytes, own entry ignored). Works with or without
+ * vgx_comm_init; when both are set the peer path is used. */
+int vgx_comm_p2p_export(vgx_ctx* ctx, uint64_t capacity_doubles, uint8_t handle[64]);
+int vgx_comm_p2p_import(vgx_ctx* ctx, int nranks, int rank, const uint8_t* handles);
 
 #ifdef __cplusplus
 }

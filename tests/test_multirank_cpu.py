@@ -25,7 +25,7 @@ blocks = []
 for (i, j) in sc.pairs:
     blocks += [(i, j), (j, i)]
 counts = [sc.submaps[a].points_xyz.shape[0] - 37 * (k % 3) for k, (a, b) in enumerate(blocks)]
-owner = api.shard_constraints(world, counts)
+owner = api.shard_constraints(world, counts, [b for (a, b) in blocks])
 layers = [o.Layer.from_blocks(s.voxel_size, s.vps, s.block_idx, s.distance, s.weight) for s in sc.submaps]
 L = o.sqrt_information(sc.odom_information)
 
@@ -85,3 +85,12 @@ def test_partition_properties():
         assert loads.max() - loads.min() <= counts.max()
         assert np.array_equal(owner, api.shard_constraints(n_ranks, counts))   # deterministic
     assert len(api.shard_constraints(4, [])) == 0
+    # locality: with keys, each rank's constraints span a contiguous key range
+    keys = rs.randint(0, 50, 300).astype(np.uint32)
+    counts = np.full(300, 1000)
+    owner = api.shard_constraints(4, counts, keys)
+    spans = [(keys[owner == r].min(), keys[owner == r].max()) for r in range(4)]
+    for r in range(3):
+        assert spans[r][1] <= spans[r + 1][0]
+    loads = np.bincount(owner, weights=counts, minlength=4)
+    assert loads.max() - loads.min() <= 1000

@@ -86,7 +86,7 @@ EXPORTS = [
     "vgx_graph_eval", "vgx_graph_eval_async", "vgx_graph_registration_costs",
     "vgx_solver_options_default", "vgx_graph_solve", "vgx_shard_constraints", "vgx_comm_unique_id",
     "vgx_comm_init",
-    "vgx_comm_destroy",
+    "vgx_comm_destroy", "vgx_comm_p2p_export", "vgx_comm_p2p_import",
 ]
 
 _lib = None
@@ -148,9 +148,11 @@ def load():
     L.vgx_solver_options_default.argtypes = [C.POINTER(SolverOptions)]
     L.vgx_solver_options_default.restype = None
     L.vgx_graph_solve.argtypes = [vp, C.POINTER(SolverOptions), pd, C.POINTER(SolverSummary)]
-    L.vgx_shard_constraints.argtypes = [i32, i32, pi32, pi32]
+    L.vgx_shard_constraints.argtypes = [i32, i32, pi32, pu32, pi32]
     L.vgx_comm_unique_id.argtypes = [pu8]
     L.vgx_comm_init.argtypes = [vp, i32, i32, pu8]
     L.vgx_comm_destroy.argtypes = [vp]
+    L.vgx_comm_p2p_export.argtypes = [vp, C.c_uint64, pu8]
+    L.vgx_comm_p2p_import.argtypes = [vp, i32, i32, pu8]
     _lib = L
     return L

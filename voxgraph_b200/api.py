@@ -248,14 +248,41 @@ class Context:
         self._check(self._L.vgx_comm_init(self._h, int(nranks), int(rank), _p(u, C.c_uint8)))
 
 
-def shard_constraints(nranks, num_residuals):
+def p2p_setup(ctx, nranks, rank, all_gather_bytes, capacity_doubles=1 << 20):
+    """Bring up the NVLink peer exchange: export this rank's buffer, all-gather the 64-byte IPC
+    handles with the caller's collective (all_gather_bytes(np.uint8[64]) -> np.uint8[nranks, 64]),
+    map the peers."""
+    h = ctx.comm_p2p_export(capacity_doubles)
+    handles = np.ascontiguousarray(all_gather_bytes(h), np.uint8).reshape(nranks, 64)
+    ctx.comm_p2p_import(nranks, rank, handles)
+
+
+def shard_constraints(nranks, num_residuals, locality_keys=None):
     """Constraint -> rank partition used by the library (host only, no GPU needed)."""
     cnt = np.ascontiguousarray(num_residuals, np.int32)
     owner = np.zeros(len(cnt), np.int32)
-    rc = _lib.load().vgx_shard_constraints(int(nranks), len(cnt), _p(cnt, C.c_int32), _p(owner, C.c_int32))
+    keys = np.ascontiguousarray(locality_keys, np.uint32) if locality_keys is not None else None
+    rc = _lib.load().vgx_shard_constraints(int(nranks), len(cnt), _p(cnt, C.c_int32),
+                                           _p(keys, C.c_uint32), _p(owner, C.c_int32))
     if rc != 0:
         raise VgxError(rc, "vgx_shard_constraints failed")
     return owner
+
+
+def _ctx_p2p_export(self, capacity_doubles):
+    h = np.zeros(64, np.uint8)
+    self._check(self._L.vgx_comm_p2p_export(self._h, int(capacity_doubles), _p(h, C.c_uint8)))
+    return h
+
+
+def _ctx_p2p_import(self, nranks, rank, handles):
+    hs = np.ascontiguousarray(handles, np.uint8).reshape(-1)
+    assert hs.size == 64 * nranks
+    self._check(self._L.vgx_comm_p2p_import(self._h, int(nranks), int(rank), _p(hs, C.c_uint8)))
+
+
+Context.comm_p2p_export = _ctx_p2p_export
+Context.comm_p2p_import = _ctx_p2p_import
 
 
 def comm_unique_id():

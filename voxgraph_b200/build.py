@@ -17,6 +17,7 @@ SOURCES = [
     ("registration.cu", ["-fmad=false"]),
     ("tsdf.cu", ["-fmad=false"]),
     ("graph.cu", []),
+    ("p2p.cu", []),
     ("nccl_dyn.cpp", []),
 ]
 

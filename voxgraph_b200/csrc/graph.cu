@@ -176,11 +176,31 @@ __device__ __forceinline__ void rel_eval(const VgxRelEdge& E, const double* __re
 // je[0..2] == -jr[0..2]; a relative-pose item is evaluated on the fly.
 // item = (source, role): source >= 0 registration constraint, < 0 relative edge -(e+1);
 // role 0: A-A, 1: B-B, 2: rows A / cols B, 3: rows B / cols A.
+// Multi-rank peer exchange: the last CTA of the assembly to finish publishes this rank's
+// partial to every peer (system-scope fence, then one flag store per rank over NVLink).
+__device__ __forceinline__ void assemble_signal(const VgxP2PSignal& sig) {
+  if (sig.nranks == 0) return;
+  __shared__ int s_sig_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_sig_last = (atomicAdd(sig.counter, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_sig_last) {
+    __threadfence_system();
+    if (threadIdx.x < sig.nranks) {
+      volatile unsigned long long* f = sig.flags[threadIdx.x] + sig.rank;
+      *f = sig.epoch;
+    }
+    if (threadIdx.x == 0) *sig.counter = 0;
+    __threadfence_system();
+  }
+}
+
 __global__ void __launch_bounds__(128)
 assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
                 const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
-                int n_rel, int exclude_reg) {
+                int n_rel, int exclude_reg, VgxP2PSignal sig) {
   // one CTA (4 warps) per output block: warp w sums items w, w+4, ... ; the four partial sums
   // are combined in warp order -> bit-reproducible
   __shared__ double s_part[4][20];
@@ -204,6 +224,7 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
       packed[0] = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
       packed[1] = 0; packed[2] = 0; packed[3] = 0;
     }
+    assemble_signal(sig);
     return;
   }
   const int i0 = csr_begin[ob], i1 = csr_begin[ob + 1];
@@ -264,6 +285,7 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
     if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
     else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
   }
+  assemble_signal(sig);
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -868,19 +890,23 @@ __global__ void lm_init_kernel(const double* __restrict__ packed, const int* __r
 }
 
 // ------------------------------------------------------------------ sharding (host only)
-extern "C" int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals, int32_t* owner) {
+extern "C" int vgx_shard_constraints(int nranks, int n, const int32_t* num_residuals,
+                                     const uint32_t* locality_keys, int32_t* owner) {
   if (nranks < 1 || n < 0 || (n > 0 && (!num_residuals || !owner))) return VGX_ERR_INVALID;
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int a, int b) { return num_residuals[a] > num_residuals[b]; });
-  std::vector<int64_t> load(nranks, 0);
+  if (locality_keys)
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return locality_keys[a] < locality_keys[b]; });
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) total += std::max(num_residuals[i], 0);
+  int64_t before = 0;
   for (int i : order) {
-    int best = 0;
-    for (int r = 1; r < nranks; ++r)
-      if (load[r] < load[best]) best = r;
-    owner[i] = best;
-    load[best] += num_residuals[i];
+    const int64_t cnt = std::max(num_residuals[i], 0);
+    // rank whose share [r * total / nranks, (r + 1) * total / nranks) holds the midpoint
+    int r = total > 0 ? (int)(((2 * before + cnt) * nranks) / (2 * total)) : 0;
+    owner[i] = std::min(std::max(r, 0), nranks - 1);
+    before += cnt;
   }
   return VGX_OK;
 }
@@ -920,7 +946,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   }
   std::vector<int32_t> owner(P, 0), counts(P, 0);
   for (int i = 0; i < P; ++i) counts[i] = all[i].n;
-  vgx_shard_constraints(c->nranks, P, counts.data(), owner.data());
+  vgx_shard_constraints(c->nranks, P, counts.data(), g->reg_read.data(), owner.data());
   g->local.clear();
   std::vector<RegConstraintDev> cons;
   std::vector<RegTile> tiles;
@@ -1070,13 +1096,23 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
                             jacobian);
     }
   }
+  // multi-rank: assemble straight into the NVLink-exported buffer when the peer path is up
+  double* d_asm = d_packed;
+  const bool p2p = c->nranks > 1 && c->p2p_ready;
+  VgxP2PSignal sig;
+  memset(&sig, 0, sizeof(sig));
+  if (p2p) {
+    int rc = vgx_p2p_begin(c, g->packed_len, &d_asm, &sig);
+    if (rc != VGX_OK) return rc;
+  }
   {
     VgxLaunchScope s(c, 5);
     assemble_kernel<<<g->N + g->E + 1, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
-                                                     g->d_csr_items, d_packed, g->N, g->E, g->n_local,
-                                                     g->n_rel_local, do_reg ? 0 : 1);
+                                                     g->d_csr_items, d_asm, g->N, g->E, g->n_local,
+                                                     g->n_rel_local, do_reg ? 0 : 1, sig);
   }
   VGX_CUDA(c, cudaGetLastError());
+  if (p2p) return vgx_p2p_gather(c, d_packed, g->packed_len);
   return vgx_nccl_allreduce_sum_f64(c, d_packed, g->packed_len);
 }
 
@@ -1236,6 +1272,10 @@ extern "C" int vgx_graph_eval(vgx_ctx* c, int exclude_registration, double* cost
           H[(size_t)(4 * j + q) * dim + 4 * i + r] = v;
         }
     }
+  }
+  if (c->nranks > 1) {
+    rc = vgx_p2p_check(c);
+    if (rc != VGX_OK) return rc;
   }
   if (!exclude_registration && g->zero_weight) return VGX_ZERO_WEIGHT;
   return VGX_OK;
@@ -1400,6 +1440,10 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
   S.total_time_s = wall_s() - t0;
   if (xyzyaw_out) memcpy(xyzyaw_out, g->x.data(), sizeof(double) * 4 * N);
   if (summary) *summary = S;
+  if (c->nranks > 1) {
+    rc = vgx_p2p_check(c);
+    if (rc != VGX_OK) return rc;
+  }
   if (S.termination == 6) VGX_FAIL(c, VGX_ERR_INVALID, "solver failure: too many consecutive invalid steps");
   return VGX_OK;
 }

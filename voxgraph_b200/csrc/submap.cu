@@ -96,6 +96,7 @@ extern "C" void vgx_ctx_destroy(vgx_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   vgx_comm_destroy(c);
+  vgx_p2p_free(c);
   vgx_graph_free(c);
   for (auto& kv : c->submaps) free_submap(kv.second);
   if (c->d_scratch) cudaFree(c->d_scratch);

@@ -136,6 +136,12 @@ struct vgx_ctx {
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // NVLink peer exchange (CUDA IPC): region = [flags 256 B | buf0 | buf1]
+  void* p2p_base = nullptr;        // own region
+  void* p2p_peer[8] = {nullptr};   // mapped regions of all ranks (own entry = p2p_base)
+  size_t p2p_cap = 0;              // doubles per buffer
+  unsigned long long p2p_epoch = 0;
+  bool p2p_ready = false;
 
   void set_error(const std::string& e) { error = e; }
   VgxSubmap* find(uint32_t id) {
@@ -174,3 +180,17 @@ void vgx_graph_invalidate_registration(vgx_ctx* ctx);
 
 // NCCL (dlopen'ed, nccl_dyn.cpp)
 int vgx_nccl_allreduce_sum_f64(vgx_ctx* ctx, double* d_buf, size_t count);
+
+// NVLink peer exchange (p2p.cu)
+// Starts an exchange epoch: returns where to assemble this evaluation's partial and the
+// signal descriptor the producing kernel's last CTA uses to notify every peer.
+struct VgxP2PSignal {
+  unsigned long long* flags[8];  // flag array of every rank (peer-mapped)
+  unsigned long long epoch;
+  int* counter;                  // local ticket counter (finished CTAs)
+  int nranks, rank;              // nranks == 0: disabled
+};
+int vgx_p2p_begin(vgx_ctx* ctx, size_t count, double** send_buf, VgxP2PSignal* sig);
+int vgx_p2p_gather(vgx_ctx* ctx, double* d_out, size_t count);     // wait for all ranks + sum into d_out
+void vgx_p2p_free(vgx_ctx* ctx);
+int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out
