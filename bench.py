@@ -293,10 +293,11 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput: K steps in one bracket
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_load0 = time.time()
     for _ in range(max(args.warmup, 3)):
         ctx.graph_eval_async()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -316,7 +317,6 @@ def run_b200(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = r_global / (ms_step * 1e-3)
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---------------- end to end through the public call with host buffers
     e2e_steps = max(3, min(args.steps, 10))
@@ -349,6 +349,17 @@ def run_b200(args):
     k_ms, k_n = ctx.profile_get(0)
     o_ms, o_n = ctx.profile_get(5)
     ctx.profile_enable(False)
+    # keep the GPU under the same evaluation load long enough for nvidia-smi (100 ms period) to
+    # see it: the clocks line covers warm-up + the timed bracket + e2e + this sustained tail
+    t_tail = time.time()
+    while time.time() - t_tail < 0.6:
+        for _ in range(50):
+            ctx.graph_eval_async()
+        ctx.synchronize()
+    clocks = sampler.stop(t_load0, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed bracket + e2e + 0.6 s of the same evaluation loop"
+
     kern_ms = k_ms / max(k_n, 1)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

@@ -100,6 +100,57 @@ def test_emit_plane_closed_form_and_edges(ctx, oracle):
     assert 0 < no_corr.sum() < len(no_corr)
 
 
+@pytest.mark.parametrize("voxel_size,vps", [(0.1, 16), (0.05, 8), (0.4, 32)])
+def test_emit_other_voxel_sizes_and_block_sizes(ctx, oracle, voxel_size, vps):
+    """BASELINE configs[3..4] voxel sizes (0.10 m, 0.05 m) and non-default voxels_per_side."""
+    world = synth.make_world(7, size_xy=(16.0, 14.0), n_clutter=20, n_walls=2)
+    r = 3.0 if voxel_size < 0.2 else 6.0
+    a = synth.make_submap(world, 400, np.array([8.0, 7.0, 1.0, 0.2]), voxel_size, vps, r, n_points=3000)
+    b = synth.make_submap(world, 401, np.array([8.6, 7.3, 1.0, -0.4]), voxel_size, vps, r, n_points=3000)
+    for s_ in (a, b):
+        ctx.upload_synth_submap(s_)
+    layer = oracle.Layer.from_blocks(b.voxel_size, b.vps, b.block_idx, b.distance, b.weight)
+    ref = a.pose_gt + np.array([0.03, -0.02, 0.01, 0.01]); read = b.pose_gt
+    ok_o, r_o, jr_o, je_o = oracle.reg_evaluate(layer, a.points_xyz, a.points_distance, a.points_weight, ref, read)
+    ok_g, r_g, jr_g, je_g = ctx.reg_eval_emit(400, 401, ref, read)
+    assert ok_o and ok_g and (np.abs(jr_o).sum(1) > 0).sum() > 300
+    assert _bit_equal(r_g, r_o) and _bit_equal(jr_g, jr_o) and _bit_equal(je_g, je_o)
+    # and through the fused path (shared-memory block grid + octets)
+    from voxgraph_b200 import api
+    pg = api.PoseGraph(ctx); og = oracle.Graph()
+    la = oracle.Layer.from_blocks(a.voxel_size, a.vps, a.block_idx, a.distance, a.weight)
+    for sid, pose, cst in ((400, ref, True), (401, read, False)):
+        pg.addSubmapNode(api.SubmapNodeConfig(sid, pose, set_constant=cst)); og.add_node(sid, pose, constant=cst)
+    pg.addRegistrationConstraint(api.RegistrationConstraintConfig(400, 401))
+    og.add_registration(400, 401, layer, a.points_xyz, a.points_distance, a.points_weight)
+    og.add_registration(401, 400, la, b.points_xyz, b.points_distance, b.points_weight)
+    ok, cg_, gg, Hg = pg.evaluate(); ok, co, go_, Ho = og.eval()
+    assert abs(cg_ - co) <= 1e-9 * co and np.abs(Hg - Ho).max() <= 1e-7 * np.abs(Ho).max()
+
+
+def test_esdf_style_layer_observed_flag(ctx, oracle):
+    """Default voxgraph registers against the ESDF (use_esdf_distance = true): the layer is uploaded
+    with weight = observed ? 1 : 0 and euclidean (untruncated) distances."""
+    rs = np.random.RandomState(11)
+    fn = lambda p: np.linalg.norm(p - np.array([1.0, 0.5, 0.2]), axis=1) - 1.5   # sphere ESDF
+    idx, d, w = synth.field_layer_blocks(fn, VS, VPS, ((-1, 1), (-1, 1), (-1, 0)))
+    w = (rs.uniform(size=w.shape) > 0.02).astype(np.float32)      # 2 % unobserved voxels
+    layer = oracle.Layer.from_blocks(VS, VPS, idx, d, w)
+    ctx.submap_upload(410, VS, VPS, idx, d, w)
+    xyz = rs.uniform(-3.0, 4.0, (4000, 3)).astype(np.float32); xyz[:, 2] = rs.uniform(-2.5, 1.0, 4000)
+    ctx.submap_upload(411, VS, VPS, idx[:1], d[:1], w[:1])
+    ctx.submap_upload_points(411, 0, xyz, np.zeros(4000, np.float32), np.ones(4000, np.float32))
+    cfg = ctx.reg_config(registration_point_type=0)
+    ref = np.array([0.1, 0.0, 0.05, 0.3]); read = np.array([0.0, 0.1, 0.0, -0.2])
+    ok_o, r_o, jr_o, je_o = oracle.reg_evaluate(layer, xyz, np.zeros(4000, np.float32),
+                                                np.ones(4000, np.float32), ref, read)
+    ok_g, r_g, jr_g, je_g = ctx.reg_eval_emit(411, 410, ref, read, cfg)
+    assert ok_o and ok_g
+    nz = (np.abs(jr_o).sum(1) > 0)
+    assert 500 < nz.sum() < 3990          # some points hit unobserved corners / leave the layer
+    assert _bit_equal(r_g, r_o) and _bit_equal(jr_g, jr_o) and _bit_equal(je_g, je_o)
+
+
 def test_emit_zero_weight_and_errors(ctx, oracle):
     from voxgraph_b200 import api
     idx, d, w = synth.plane_layer_blocks([0, 0, 1.0], 0.0, VS, VPS, ((0, 0), (0, 0), (0, 0)))
