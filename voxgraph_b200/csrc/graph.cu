@@ -377,9 +377,11 @@ __global__ void lm_persist_kernel(const double* __restrict__ packed, const int* 
 // 1/sqrt(d) to double precision from the float MUFU seed + Newton (the fp64 sqrt/div
 // routines cost several hundred cycles each on the serial pivot path).
 __device__ __forceinline__ double fast_rsqrt(double d) {
+  // rsqrtf is good to ~2^-22; each Newton step squares the error: two steps reach double precision
   double r = (double)rsqrtf((float)d);
+  const double hd = -0.5 * d;
 #pragma unroll
-  for (int it = 0; it < 3; ++it) r = r * fma(-0.5 * d, r * r, 1.5);
+  for (int it = 0; it < 3; ++it) r = r * fma(hd, r * r, 1.5);
   return r;
 }
 
@@ -527,24 +529,32 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
       }
     }
     __syncthreads();
-    // (2) factor the diagonal block (warp 0; lane = row inside the block)
+    // (2) factor the diagonal block: warp 0, lane r holds row r of the 8x8 block in registers,
+    //     pivots and multipliers travel by shuffle (no shared-memory round trips on the serial path)
     if (warp == 0) {
-      for (int k = 0; k < nb; ++k) {
-        const int ok = tri_off(J0 + k, M);
-        double d = S[ok];
-        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = 1; d = 1.0; }
-        const double rs = fast_rsqrt(d);
-        __syncwarp();
-        if (lane == k) { S[ok] = d * rs; rinv[J0 + k] = rs; }
-        if (lane > k && lane < nb) S[ok + lane - k] *= rs;
-        __syncwarp();
-        if (lane > k && lane < nb) {
-          const double lrk = S[ok + lane - k];
-          for (int c = k + 1; c <= lane; ++c)
-            S[tri_off(J0 + c, M) + lane - c] -= lrk * S[ok + c - k];
+      double row[CS_NB];
+#pragma unroll
+      for (int c = 0; c < CS_NB; ++c)
+        row[c] = (lane < nb && c <= lane && c < nb) ? S[tri_off(J0 + c, M) + lane - c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < CS_NB; ++k) {
+        if (k < nb) {
+          double d = __shfl_sync(0xffffffffu, row[k], k);
+          if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = 1; d = 1.0; }
+          const double rs = fast_rsqrt(d);
+          if (lane == k) { row[k] = d * rs; rinv[J0 + k] = rs; }
+          else if (lane > k) row[k] *= rs;
+          const double lik = row[k];
+#pragma unroll
+          for (int c = k + 1; c < CS_NB; ++c) {
+            const double lck = __shfl_sync(0xffffffffu, lik, c);  // L[c][k]
+            if (lane >= c) row[c] = fma(-lik, lck, row[c]);
+          }
         }
-        __syncwarp();
       }
+#pragma unroll
+      for (int c = 0; c < CS_NB; ++c)
+        if (lane < nb && c <= lane && c < nb) S[tri_off(J0 + c, M) + lane - c] = row[c];
     }
     __syncthreads();
     // (3) panel solve: rows below the block (incl. the rhs row n)

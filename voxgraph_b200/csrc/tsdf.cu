@@ -230,12 +230,15 @@ __device__ __forceinline__ void tsdf_update_terms(const TsdfParams& P, const flo
 // voxel is left untouched (new_weight < kFloatEpsilon).
 __device__ __forceinline__ bool tsdf_apply(float trunc, float max_weight, float sdf, float uw,
                                            float& vd, float& vw) {
+  // branch-free: the long-segment replay runs tens of thousands of these back to back
   const float new_weight = vw + uw;
-  if (new_weight < VGX_EPS) return false;
+  const bool skip = new_weight < VGX_EPS;
   const float new_sdf = (sdf * uw + vd * vw) / new_weight;
-  vd = (new_sdf > 0.0f) ? fminf(trunc, new_sdf) : fmaxf(-trunc, new_sdf);
-  vw = fminf(max_weight, new_weight);
-  return true;
+  const float nd = (new_sdf > 0.0f) ? fminf(trunc, new_sdf) : fmaxf(-trunc, new_sdf);
+  const float nw = fminf(max_weight, new_weight);
+  vd = skip ? vd : nd;
+  vw = skip ? vw : nw;
+  return !skip;
 }
 
 __device__ __forceinline__ void update_tsdf_voxel(const TsdfParams& P, const float origin[3],
@@ -358,18 +361,37 @@ tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restri
   const unsigned head = long_heads[w];
   const unsigned key = keys[head];
   float2 v = dw[key];
+  // software pipeline: the next batch's tuples are in flight while the current batch is replayed
+  unsigned j = head + lane;
+  bool mine = j < total && keys[j] == key;
+  float2 u = mine ? vals[j] : make_float2(0.f, 0.f);
   for (unsigned base = head; base < total; base += 32) {
-    const unsigned j = base + lane;
-    const bool mine = j < total && keys[j] == key;
-    const float2 u = mine ? vals[j] : make_float2(0.f, 0.f);
+    const unsigned jn = base + 32 + lane;
+    const bool mine_n = jn < total && keys[jn] == key;
+    const float2 u_n = mine_n ? vals[jn] : make_float2(0.f, 0.f);
     const unsigned m = __ballot_sync(0xffffffffu, mine);
     const int cnt = __popc(m);  // the matching lanes form a prefix (keys are sorted)
-    for (int k = 0; k < cnt; ++k) {
-      const float sx = __shfl_sync(0xffffffffu, u.x, k);
-      const float sy = __shfl_sync(0xffffffffu, u.y, k);
-      tsdf_apply(trunc, max_weight, sx, sy, v.x, v.y);
+    if (cnt == 32) {
+      // full batch: stage all 32 tuples in registers first so the shuffles stay off the
+      // serial (distance, weight) recurrence
+      float sx[32], sy[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        sx[k] = __shfl_sync(0xffffffffu, u.x, k);
+        sy[k] = __shfl_sync(0xffffffffu, u.y, k);
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) tsdf_apply(trunc, max_weight, sx[k], sy[k], v.x, v.y);
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        const float sx = __shfl_sync(0xffffffffu, u.x, k);
+        const float sy = __shfl_sync(0xffffffffu, u.y, k);
+        tsdf_apply(trunc, max_weight, sx, sy, v.x, v.y);
+      }
+      break;
     }
-    if (cnt < 32) break;
+    mine = mine_n;
+    u = u_n;
   }
   if (lane == 0) dw[key] = v;
 }
