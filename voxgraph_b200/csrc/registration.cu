@@ -84,12 +84,32 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
     double d0 = 0.0, d1 = 0.0;
     const int end = T.start + T.count;
     const size_t vox_shift = 3 * C.vps_shift;
+#if VGX_REG_PREFETCH
+    // software pipeline: the next round's point is loaded while this round is computed
+    float nx, ny, nz, nd, nw;
+    {
+      const int i0 = T.start + threadIdx.x;
+      const int ic0 = i0 < end ? i0 : T.start;
+      nx = __ldg(C.px + ic0); ny = __ldg(C.py + ic0); nz = __ldg(C.pz + ic0);
+      nd = __ldg(C.pd + ic0); nw = __ldg(C.pw + ic0);
+    }
+#endif
     for (int base = T.start; base < end; base += VGX_REG_THREADS) {
       const int i = base + threadIdx.x;
       const bool act = i < end;
+#if VGX_REG_PREFETCH
+      const float xi = nx, yi = ny, zi = nz, dist = nd, w = nw;
+      {
+        const int in = i + VGX_REG_THREADS;
+        const int icn = in < end ? in : T.start;
+        nx = __ldg(C.px + icn); ny = __ldg(C.py + icn); nz = __ldg(C.pz + icn);
+        nd = __ldg(C.pd + icn); nw = __ldg(C.pw + icn);
+      }
+#else
       const int ic = act ? i : T.start;
       const float xi = __ldg(C.px + ic), yi = __ldg(C.py + ic), zi = __ldg(C.pz + ic);
       const float dist = __ldg(C.pd + ic), w = __ldg(C.pw + ic);
+#endif
       float p0, p1, p2;
       vgx_reg_transform(P, xi, yi, zi, p0, p1, p2);
       RegLocate L;
@@ -104,7 +124,12 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       const bool found = slot >= 0;
       const size_t lin = ((size_t)(found ? slot : 0) << vox_shift) + L.lin;
       const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
+#if VGX_REG_STREAM_OCTETS
+      // an octet is touched once per evaluation: keep it out of L1 (evict-first)
+      const float4 lo = __ldcs(o), hi = __ldcs(o + 1);
+#else
       const float4 lo = __ldg(o), hi = __ldg(o + 1);
+#endif
       const float d[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       const bool ok = found && vgx_octet_ok(d);
       const RegPointResult R = vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, L.ox, L.oy, L.oz);

@@ -8,7 +8,13 @@ struct RegPoseConst;
 
 #define VGX_REG_THREADS 256
 #ifndef VGX_REG_MIN_BLOCKS
-#define VGX_REG_MIN_BLOCKS 4       // resident CTAs per SM the register budget is sized for
+#define VGX_REG_MIN_BLOCKS 3       // resident CTAs per SM the register budget is sized for
+#endif
+#ifndef VGX_REG_PREFETCH
+#define VGX_REG_PREFETCH 0         // software-pipelined point loads
+#endif
+#ifndef VGX_REG_STREAM_OCTETS
+#define VGX_REG_STREAM_OCTETS 0   // ld.global.cs for the octet fetch
 #endif
 #define VGX_REG_NSUM 21            // 15 (upper 5x5) + 5 (gradient) + 1 (cost)
 #define VGX_REG_NSTRIDE 24
