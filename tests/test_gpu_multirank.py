@@ -89,7 +89,7 @@ assert np.abs(x1 - x3).max() < 1e-6, np.abs(x1 - x3).max()
 xt = torch.from_numpy(x3).cuda(); x0 = xt.clone(); dist.broadcast(x0, 0)
 assert torch.equal(xt, x0)
 dist.barrier()
-print("rank", rank, "multirank ok", local, glob, s2.iterations, s3.iterations)
+sys.stdout.write("rank-%d-multirank-ok %d %d %d %d\n" % (rank, local, glob, s2.iterations, s3.iterations)); sys.stdout.flush()
 peer.close(); multi.close(); single.close()
 dist.destroy_process_group()
 '''
@@ -107,4 +107,4 @@ def test_two_gpu_nccl_allreduce_matches_single(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
     p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-4000:]
-    assert p.stdout.count("multirank ok") == 2, p.stdout[-4000:]
+    assert "rank-0-multirank-ok" in p.stdout and "rank-1-multirank-ok" in p.stdout, p.stdout[-4000:]
