@@ -88,6 +88,20 @@ x3 = np.array([pg3.getSubmapPoses()[i] for i in range(len(sc.submaps))])
 assert np.abs(x1 - x3).max() < 1e-6, np.abs(x1 - x3).max()
 xt = torch.from_numpy(x3).cuda(); x0 = xt.clone(); dist.broadcast(x0, 0)
 assert torch.equal(xt, x0)
+# ---- one-launch variant: assemble + signal + wait + gather-sum fused in a persistent kernel
+os.environ["VGX_P2P_FUSED"] = "1"
+fused = api.Context(lr)
+api.p2p_setup(fused, world, rank, all_gather_bytes, capacity_doubles=1 << 16)
+pg4 = build(fused)
+for rep in range(4):
+    ok, c4, g4, H4 = pg4.evaluate()
+    assert c4 == c3 and np.array_equal(g4, g3) and np.array_equal(H4, H3)   # same sums, same order
+pg4.solver_options = fused.solver_options(**opts)
+s4 = pg4.optimize()
+x4 = np.array([pg4.getSubmapPoses()[i] for i in range(len(sc.submaps))])
+assert np.array_equal(x4, x3) and s4.iterations == s3.iterations
+os.environ["VGX_P2P_FUSED"] = "0"
+fused.close()
 dist.barrier()
 sys.stdout.write("rank-%d-multirank-ok %d %d %d %d\n" % (rank, local, glob, s2.iterations, s3.iterations)); sys.stdout.flush()
 peer.close(); multi.close(); single.close()

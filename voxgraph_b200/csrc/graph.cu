@@ -6,6 +6,7 @@
 // include/voxgraph/backend/constraint/cost_functions/relative_pose_cost_function_inl.h:8-70,
 // src/backend/node/node_collection.cpp:8-12 (x,y,z additive, yaw wrapped),
 // Ceres 1.x TrustRegionMinimizer/LevenbergMarquardtStrategy defaults.
+#include <limits.h>
 #include <math.h>
 #include <string.h>
 #include <time.h>
@@ -196,15 +197,16 @@ __device__ __forceinline__ void assemble_signal(const VgxP2PSignal& sig) {
   }
 }
 
-__global__ void __launch_bounds__(128)
-assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
-                const double* __restrict__ x, const int* __restrict__ csr_begin,
-                const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
-                int n_rel, int exclude_reg, VgxP2PSignal sig) {
-  // one CTA (4 warps) per output block: warp w sums items w, w+4, ... ; the four partial sums
-  // are combined in warp order -> bit-reproducible
-  __shared__ double s_part[4][20];
-  const int ob = blockIdx.x;
+// Work of one output block `ob` (N diagonal, E off-diagonal, ob == N + E: the cost) by one
+// 4-warp CTA: warp w sums items w, w+4, ...; the four partial sums are combined in warp order
+// -> bit-reproducible. Ends with a __syncthreads() so it can be called in a loop.
+__device__ __forceinline__ void assemble_block(int ob, const double* __restrict__ csum,
+                                               const VgxRelEdge* __restrict__ rel,
+                                               const double* __restrict__ x,
+                                               const int* __restrict__ csr_begin,
+                                               const int2* __restrict__ items,
+                                               double* __restrict__ packed, int N, int E, int n_reg,
+                                               int n_rel, int exclude_reg, double (*s_part)[20]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ob == N + E) {
     // cost = 1/2 sum r^2
@@ -224,7 +226,7 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
       packed[0] = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
       packed[1] = 0; packed[2] = 0; packed[3] = 0;
     }
-    assemble_signal(sig);
+    __syncthreads();
     return;
   }
   const int i0 = csr_begin[ob], i1 = csr_begin[ob + 1];
@@ -285,7 +287,59 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
     if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
     else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128)
+assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
+                const double* __restrict__ x, const int* __restrict__ csr_begin,
+                const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
+                int n_rel, int exclude_reg, VgxP2PSignal sig) {
+  __shared__ double s_part[4][20];
+  assemble_block(blockIdx.x, csum, rel, x, csr_begin, items, packed, N, E, n_reg, n_rel, exclude_reg, s_part);
   assemble_signal(sig);
+}
+
+// Fused compute + collective (multi-rank, peer exchange): ONE launch assembles this rank's
+// partial into its NVLink-exported buffer, publishes it to every peer, waits for the peers and
+// sums all partials in rank order straight out of peer memory.  The grid is persistent and
+// sized to be fully co-resident, so waiting CTAs can never starve a CTA that still has to
+// produce: phase 1 never waits, phase 2 only waits on flags that phase 1 of every rank sets.
+struct VgxP2PGather {
+  const double* buf[8];  // this epoch's buffer of every rank (peer-mapped)
+  int* timeout_flag;
+};
+
+__global__ void __launch_bounds__(128)
+assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
+                         const double* __restrict__ x, const int* __restrict__ csr_begin,
+                         const int2* __restrict__ items, double* __restrict__ send, int N, int E,
+                         int n_reg, int n_rel, int exclude_reg, VgxP2PSignal sig, VgxP2PGather gat,
+                         double* __restrict__ out, int count) {
+  __shared__ double s_part[4][20];
+  __shared__ int s_ok;
+  for (int ob = blockIdx.x; ob <= N + E; ob += gridDim.x)
+    assemble_block(ob, csum, rel, x, csr_begin, items, send, N, E, n_reg, n_rel, exclude_reg, s_part);
+  assemble_signal(sig);
+  // ---- phase 2: wait for every rank's flag in OUR region, then gather-sum our slice
+  if (threadIdx.x == 0) {
+    const volatile unsigned long long* mine = sig.flags[sig.rank];
+    const long long t0 = clock64();
+    int ok = 1;
+    for (int r = 0; r < sig.nranks && ok; ++r)
+      while (mine[r] < sig.epoch)
+        if (clock64() - t0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer is gone
+    __threadfence_system();
+    s_ok = ok;
+    if (!ok) *gat.timeout_flag = 1;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < sig.nranks; ++r) s += *((const volatile double*)(gat.buf[r] + i));
+    out[i] = s;
+  }
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -1114,6 +1168,32 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   if (p2p) {
     int rc = vgx_p2p_begin(c, g->packed_len, &d_asm, &sig);
     if (rc != VGX_OK) return rc;
+  }
+  if (p2p && c->p2p_fused && g->packed_len < (size_t)INT_MAX) {
+    // one launch: assemble -> signal -> wait -> gather-sum (grid fully co-resident)
+    static int resident = 0;
+    if (resident == 0) {
+      int sms = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_exchange_kernel, 128, 0) != cudaSuccess)
+        per_sm = 1;
+      resident = std::max(1, sms * std::max(per_sm, 1));
+    }
+    VgxP2PGather gat;
+    memset(&gat, 0, sizeof(gat));
+    const void* bufs[8];
+    vgx_p2p_gather_sources(c, bufs, &gat.timeout_flag);
+    for (int r = 0; r < c->nranks; ++r) gat.buf[r] = (const double*)bufs[r];
+    const int grid = std::min(g->N + g->E + 1, std::min(resident, 592));
+    {
+      VgxLaunchScope s(c, 5);
+      assemble_exchange_kernel<<<grid, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
+                                                    g->d_csr_items, d_asm, g->N, g->E, g->n_local,
+                                                    g->n_rel_local, do_reg ? 0 : 1, sig, gat, d_packed,
+                                                    (int)g->packed_len);
+    }
+    VGX_CUDA(c, cudaGetLastError());
+    return VGX_OK;
   }
   {
     VgxLaunchScope s(c, 5);

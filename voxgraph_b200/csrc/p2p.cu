@@ -8,6 +8,7 @@
 //                        ranks 0..n-1 in rank order straight out of peer memory (ld.volatile, no L1)
 // Two buffers suffice: a rank can only signal epoch e+1 after its own gather of e has finished
 // (stream order), and nobody passes the gather of e+1 before everybody signalled e+1.
+#include <stdlib.h>
 #include <string.h>
 
 #include "vgx_internal.h"
@@ -93,6 +94,11 @@ extern "C" int vgx_comm_p2p_import(vgx_ctx* c, int nranks, int rank, const uint8
   c->nranks = nranks;
   c->rank = rank;
   c->p2p_ready = true;
+  {
+    // the one-launch path is opt-in until it has been validated on every rank count
+    const char* f = getenv("VGX_P2P_FUSED");
+    c->p2p_fused = f && f[0] == '1';
+  }
   vgx_graph_invalidate_registration(c);
   return VGX_OK;
 }
@@ -118,6 +124,14 @@ int vgx_p2p_begin(vgx_ctx* c, size_t count, double** send_buf, VgxP2PSignal* sig
   sig->counter = (int*)((char*)c->p2p_base + 192);  // local word of the flag page
   for (int r = 0; r < c->nranks; ++r) sig->flags[r] = (unsigned long long*)c->p2p_peer[r];
   return VGX_OK;
+}
+
+void vgx_p2p_gather_sources(vgx_ctx* c, const void* bufs[8], int** timeout_flag) {
+  const unsigned long long e = c->p2p_epoch;
+  for (int r = 0; r < 8; ++r)
+    bufs[r] = r < c->nranks ? (const void*)((double*)((char*)c->p2p_peer[r] + P2P_FLAG_BYTES) + (e & 1) * c->p2p_cap)
+                            : nullptr;
+  *timeout_flag = (int*)((char*)c->p2p_base + 128);
 }
 
 int vgx_p2p_gather(vgx_ctx* c, double* d_out, size_t count) {

@@ -142,6 +142,7 @@ struct vgx_ctx {
   size_t p2p_cap = 0;              // doubles per buffer
   unsigned long long p2p_epoch = 0;
   bool p2p_ready = false;
+  bool p2p_fused = false;          // one-launch assemble + exchange (VGX_P2P_FUSED=1)
 
   void set_error(const std::string& e) { error = e; }
   VgxSubmap* find(uint32_t id) {
@@ -192,5 +193,7 @@ struct VgxP2PSignal {
 };
 int vgx_p2p_begin(vgx_ctx* ctx, size_t count, double** send_buf, VgxP2PSignal* sig);
 int vgx_p2p_gather(vgx_ctx* ctx, double* d_out, size_t count);     // wait for all ranks + sum into d_out
+// current epoch's buffer of every rank + the local timeout word (for the fused kernel)
+void vgx_p2p_gather_sources(vgx_ctx* ctx, const void* bufs[8], int** timeout_flag);
 void vgx_p2p_free(vgx_ctx* ctx);
 int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out
