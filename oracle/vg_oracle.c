@@ -14,6 +14,7 @@
 #include <time.h>
 #include <pthread.h>
 #include <stdatomic.h>
+#include <stdint.h>
 
 #define VGO_COORD_EPS 1e-6f  /* voxblox kCoordinateEpsilon */
 #define VGO_FLOAT_EPS 1e-6f  /* voxblox kFloatEpsilon / kEpsilon */
@@ -576,12 +577,74 @@ typedef struct {
   atomic_int next;
 } reg_job;
 
+/* Persistent worker pool: Ceres keeps its evaluation threads alive between iterations, so the
+ * baseline must not pay thread creation per evaluation. Workers sleep on a condition variable;
+ * an evaluation publishes a job, wakes them and waits until all have finished. */
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t wake, done;
+  pthread_t* threads;
+  int n_threads;      /* workers created so far */
+  int active;         /* workers taking part in the current job */
+  int remaining;      /* workers that have not finished the current job */
+  unsigned long generation;
+  void* (*fn)(void*);
+  void* arg;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+            NULL, 0, 0, 0, 0, NULL, NULL};
+
+static void* pool_main(void* p) {
+  const int id = (int)(intptr_t)p;
+  unsigned long seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.generation == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+    seen = g_pool.generation;
+    if (id >= g_pool.active) continue;
+    void* (*fn)(void*) = g_pool.fn;
+    void* arg = g_pool.arg;
+    pthread_mutex_unlock(&g_pool.mu);
+    fn(arg);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.remaining == 0) pthread_cond_signal(&g_pool.done);
+  }
+  return NULL;
+}
+
+/* Runs fn(arg) on nt pool threads and returns when all are done. */
+static void pool_run(int nt, void* (*fn)(void*), void* arg) {
+  pthread_mutex_lock(&g_pool.mu);
+  if (nt > g_pool.n_threads) {
+    g_pool.threads = (pthread_t*)realloc(g_pool.threads, sizeof(pthread_t) * nt);
+    for (int t = g_pool.n_threads; t < nt; ++t) {
+      pthread_create(&g_pool.threads[t], NULL, pool_main, (void*)(intptr_t)t);
+      pthread_detach(g_pool.threads[t]);
+    }
+    g_pool.n_threads = nt;
+  }
+  g_pool.fn = fn; g_pool.arg = arg;
+  g_pool.active = nt; g_pool.remaining = nt;
+  g_pool.generation++;
+  pthread_cond_broadcast(&g_pool.wake);
+  while (g_pool.remaining > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+}
+
 static void* reg_worker(void* arg) {
   reg_job* job = (reg_job*)arg;
   vgo_graph* g = job->g;
   const int kmax = job->kmax, want_j = job->want_j;
-  double* r = (double*)malloc(sizeof(double) * (size_t)(kmax > 0 ? kmax : 1));
-  double* J = want_j ? (double*)malloc(sizeof(double) * 8 * (size_t)(kmax > 0 ? kmax : 1)) : NULL;
+  /* per-thread scratch survives between evaluations (Ceres preallocates its Jacobian too) */
+  static __thread double* tl_buf = NULL;
+  static __thread size_t tl_cap = 0;
+  const size_t need = 9 * (size_t)(kmax > 0 ? kmax : 1);
+  if (need > tl_cap) {
+    free(tl_buf);
+    tl_buf = (double*)malloc(sizeof(double) * need);
+    tl_cap = need;
+  }
+  double* r = tl_buf;
+  double* J = want_j ? tl_buf + (size_t)(kmax > 0 ? kmax : 1) : NULL;
   for (;;) {
     const int e = atomic_fetch_add(&job->next, 1);
     if (e >= g->n_reg) break;
@@ -610,7 +673,6 @@ static void* reg_worker(void* arg) {
     for (int a = 0; a < 8; ++a)
       for (int b = 0; b < a; ++b) o[8 * a + b] = o[8 * b + a];
   }
-  free(r); free(J);
   return NULL;
 }
 
@@ -662,10 +724,7 @@ static int graph_eval_at(vgo_graph* g, const double* x, int num_threads, int exc
     if (nt <= 1) {
       reg_worker(&job);
     } else {
-      pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
-      for (int t = 0; t < nt; ++t) pthread_create(&th[t], NULL, reg_worker, &job);
-      for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
-      free(th);
+      pool_run(nt, reg_worker, &job);
     }
     for (int e = 0; e < g->n_reg; ++e) {
       const reg_edge* ge = &g->reg[e];
