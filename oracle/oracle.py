@@ -115,6 +115,7 @@ def lib():
     L.vgo_reg_pose_setup.argtypes = [f64p, f64p, f32p, f32p]
     L.vgo_relpose_evaluate.argtypes = [f64p, f64p, f64p, C.c_double, f64p, f64p, f64p, f64p]
     L.vgo_sqrt_information.argtypes = [f64p, f64p]
+    L.vgo_sqrt_information_ldlt.argtypes = [f64p, f64p]
     L.vgo_normalize_angle.restype = C.c_double
     L.vgo_normalize_angle.argtypes = [C.c_double]
     L.vgo_solver_options_default.argtypes = [C.POINTER(SolverOptions)]
@@ -256,6 +257,16 @@ def sqrt_information(info):
     rc = lib().vgo_sqrt_information(_p(info, C.c_double), _p(out, C.c_double))
     if rc != 0:
         raise ValueError("information matrix not positive definite")
+    return out.reshape(4, 4)
+
+
+def sqrt_information_ldlt(info):
+    """allow_semi_definite_information_matrix branch (constraint.cpp:15-37)."""
+    info = f64(info).reshape(16)
+    out = np.zeros(16)
+    rc = lib().vgo_sqrt_information_ldlt(_p(info, C.c_double), _p(out, C.c_double))
+    if rc != 0:
+        raise ValueError("information matrix must be positive semi-definite")
     return out.reshape(4, 4)
 
 

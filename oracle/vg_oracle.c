@@ -475,6 +475,56 @@ int vgo_sqrt_information(const double info[16], double L[16]) {
   return 0;
 }
 
+/* Constraint ctor, LDLT branch (constraint.cpp:15-37). Eigen's LDLT (lower, in place) picks
+ * the largest remaining |diagonal| as pivot and applies it as a symmetric transposition. */
+int vgo_sqrt_information_ldlt(const double info[16], double S[16]) {
+  double A[4][4];
+  int tr[4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) A[i][j] = info[4 * i + j];
+  int sign_pos = 1;
+  for (int k = 0; k < 4; ++k) {
+    int piv = k;
+    double best = fabs(A[k][k]);
+    for (int i = k + 1; i < 4; ++i)
+      if (fabs(A[i][i]) > best) { best = fabs(A[i][i]); piv = i; }
+    tr[k] = piv;
+    if (piv != k) {
+      /* symmetric swap of rows/columns k and piv (full matrix kept symmetric) */
+      for (int j = 0; j < 4; ++j) { double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
+      for (int i = 0; i < 4; ++i) { double t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
+    }
+    /* eliminate: A = L D L^T step on the trailing block */
+    const double d = A[k][k];
+    if (d < -1e-12 * (1.0 + best)) sign_pos = 0;
+    if (fabs(d) > 0) {
+      for (int i = k + 1; i < 4; ++i) A[i][k] /= d;
+      for (int i = k + 1; i < 4; ++i)
+        for (int j = k + 1; j < 4; ++j) A[i][j] -= A[i][k] * d * A[j][k];
+    } else {
+      for (int i = k + 1; i < 4; ++i) A[i][k] = 0;
+    }
+    for (int j = k + 1; j < 4; ++j) A[k][j] = 0; /* keep L strictly lower */
+  }
+  if (!sign_pos) return -1;
+  /* M = L * sqrt(D) */
+  double M[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const double l = (i == j) ? 1.0 : (i > j ? A[i][j] : 0.0);
+      const double d = A[j][j] > 0 ? sqrt(A[j][j]) : 0.0;
+      M[i][j] = l * d;
+    }
+  /* S = P^T M P with P = product of the transpositions (applied in order) */
+  int perm[4] = {0, 1, 2, 3};
+  for (int k = 0; k < 4; ++k) { int t = perm[k]; perm[k] = perm[tr[k]]; perm[tr[k]] = t; }
+  /* (P x)[k] = x[perm[k]]  =>  S[perm[i]][perm[j]] = M[i][j] */
+  memset(S, 0, sizeof(double) * 16);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) S[4 * perm[i] + perm[j]] = M[i][j];
+  return 0;
+}
+
 /* ========================================================================= */
 /* Pose graph + LM                                                           */
 /* ========================================================================= */

@@ -104,6 +104,10 @@ void vgo_relpose_evaluate(const double pose_a[4], const double pose_b[4], const 
 /* Constraint ctor (src/backend/constraint/constraint.cpp:4-38): LLT lower factor.
  * Returns 0 ok, -1 not positive definite. */
 int vgo_sqrt_information(const double info[16], double sqrt_info[16]);
+/* Constraint ctor, allow_semi_definite_information_matrix branch (constraint.cpp:15-37):
+ * Eigen LDLT with diagonal pivoting; sqrt_information = P^T L sqrt(D) P.
+ * Returns 0 ok, -1 if the matrix is not positive semi-definite. */
+int vgo_sqrt_information_ldlt(const double info[16], double sqrt_info[16]);
 /* NormalizeAngle (include/voxgraph/backend/local_parameterization/normalize_angle.h:11-16) */
 double vgo_normalize_angle(double a);
 

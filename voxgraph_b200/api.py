@@ -310,6 +310,59 @@ class RelativePoseConstraintConfig:   # relative_pose_constraint.h:13-18
 
 
 @dataclass
+class ReferenceFrameNodeConfig:       # ReferenceFrameNode::Config (reference_frame_node.h:15-17)
+    reference_frame_id: int
+    T_mission_node_initial: np.ndarray = field(default_factory=lambda: np.zeros(4))
+    set_constant: bool = True
+
+
+@dataclass
+class AbsolutePoseConstraintConfig:   # absolute_pose_constraint.h:13-18
+    reference_frame_id: int
+    submap_id: int
+    T_ref_submap: np.ndarray          # [tx, ty, tz, yaw]
+    information_matrix: np.ndarray = field(default_factory=lambda: np.eye(4))
+    allow_semi_definite_information_matrix: bool = False
+
+
+def sqrt_information_matrix(information_matrix, allow_semi_definite=False):
+    """Constraint ctor (constraint.cpp:4-38): the LLT lower factor, or for semi-definite matrices
+    Eigen's pivoted LDLT, sqrt = P^T L sqrt(D) P. Raises like the reference CHECKs."""
+    info = np.asarray(information_matrix, np.float64).reshape(4, 4)
+    if not allow_semi_definite:
+        try:
+            return np.linalg.cholesky(info)
+        except np.linalg.LinAlgError:
+            raise ValueError("The square root of the information matrix could not be computed, "
+                             "make sure it is symmetric and positive definite")
+    A = info.copy()
+    perm = np.arange(4)
+    for k in range(4):
+        piv = k + int(np.argmax(np.abs(np.diag(A)[k:])))
+        if piv != k:
+            A[[k, piv], :] = A[[piv, k], :]
+            A[:, [k, piv]] = A[:, [piv, k]]
+            perm[[k, piv]] = perm[[piv, k]]
+        d = A[k, k]
+        if d < -1e-12 * (1.0 + np.abs(np.diag(info)).max()):
+            raise ValueError("The information matrix must be positive semi-definite")
+        if abs(d) > 0:
+            A[k + 1:, k] /= d
+            A[k + 1:, k + 1:] -= np.outer(A[k + 1:, k], A[k + 1:, k]) * d
+        else:
+            A[k + 1:, k] = 0
+        A[k, k + 1:] = 0
+    Lm = np.tril(A, -1) + np.eye(4)
+    M = Lm * np.sqrt(np.maximum(np.diag(A), 0.0))[None, :]
+    S = np.zeros((4, 4))
+    S[np.ix_(perm, perm)] = M
+    return S
+
+
+FRAME_NODE_ID_BASE = 0x80000000   # reference-frame nodes share the C-ABI's uint32 node id space
+
+
+@dataclass
 class RegistrationConstraintConfig:   # registration_constraint.h:15-21
     first_submap_id: int
     second_submap_id: int
@@ -326,6 +379,7 @@ class PoseGraph:
     def __init__(self, ctx):
         self.ctx = ctx
         self._nodes = {}
+        self._frames = set()
         self._relative = []
         self._registration = []   # (ref_id, read_id) residual blocks, mirrored ones included
         self._reg_cfg = None
@@ -341,14 +395,34 @@ class PoseGraph:
     def hasSubmapNode(self, submap_id):
         return int(submap_id) in self._nodes
 
+    def addReferenceFrameNode(self, config):
+        """pose_graph.cpp:21-24; the frame node lives at id FRAME_NODE_ID_BASE + frame id."""
+        nid = FRAME_NODE_ID_BASE + int(config.reference_frame_id)
+        self._nodes[nid] = [np.asarray(config.T_mission_node_initial, np.float64).copy(),
+                            bool(config.set_constant)]
+        self._frames.add(int(config.reference_frame_id))
+        self._dirty = True
+
+    def hasReferenceFrameNode(self, frame_id):
+        return int(frame_id) in self._frames
+
+    def addAbsolutePoseConstraint(self, config):
+        """pose_graph.cpp:33-39 + absolute_pose_constraint.cpp:6-35: a RelativePoseCostFunction between
+        the reference-frame node and the submap node (e.g. the height constraint, information zz only)."""
+        if int(config.reference_frame_id) not in self._frames:
+            raise ValueError("Graph contains no reference frame node %d" % int(config.reference_frame_id))
+        if int(config.submap_id) not in self._nodes:
+            raise ValueError("Graph contains no node for submap %d" % int(config.submap_id))
+        L = sqrt_information_matrix(config.information_matrix,
+                                    config.allow_semi_definite_information_matrix)
+        self._relative.append((FRAME_NODE_ID_BASE + int(config.reference_frame_id), int(config.submap_id),
+                               np.asarray(config.T_ref_submap, np.float64).copy(), L))
+        self._dirty = True
+
     def addRelativePoseConstraint(self, config):
-        info = np.asarray(config.information_matrix, np.float64)
         # Constraint ctor (constraint.cpp:8-14): LLT lower factor, CHECK on failure
-        try:
-            L = np.linalg.cholesky(info)
-        except np.linalg.LinAlgError:
-            raise ValueError("The square root of the information matrix could not be computed, "
-                             "make sure it is symmetric and positive definite")
+        L = sqrt_information_matrix(config.information_matrix,
+                                    getattr(config, "allow_semi_definite_information_matrix", False))
         self._relative.append((int(config.origin_submap_id), int(config.destination_submap_id),
                                np.asarray(config.T_origin_destination, np.float64).copy(), L))
         self._dirty = True
@@ -409,7 +483,7 @@ class PoseGraph:
         return self.ctx.graph_eval(len(ids), exclude_registration_constraints, want_H)
 
     def getSubmapPoses(self):
-        return {i: v[0].copy() for i, v in self._nodes.items()}
+        return {i: v[0].copy() for i, v in self._nodes.items() if i < FRAME_NODE_ID_BASE}
 
     def getSolverSummaries(self):
         return self.solver_summaries
