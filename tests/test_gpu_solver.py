@@ -199,6 +199,48 @@ def test_large_relative_pose_graph(ctx, oracle, n):
     assert abs(s.iterations - so.iterations) <= 1
 
 
+def test_height_constraints_via_reference_frame(ctx, oracle):
+    """AbsolutePoseConstraint (height measurement, information only on z; LDLT sqrt) between a
+    constant reference-frame node and submap nodes, mixed with odometry."""
+    from voxgraph_b200 import api
+    rs = np.random.RandomState(5)
+    n = 6
+    gt = np.stack([np.arange(n) * 2.0, np.sin(np.arange(n)), np.linspace(0.5, 1.5, n), np.linspace(0, 1, n)], -1)
+    info_odo = np.diag([1.0, 1.0, 2500.0, 2500.0])
+    info_h = np.zeros((4, 4)); info_h[2, 2] = 2500.0
+    pg = api.PoseGraph(ctx); og = oracle.Graph()
+    pg.addReferenceFrameNode(api.ReferenceFrameNodeConfig(0))
+    og.add_node(api.FRAME_NODE_ID_BASE, np.zeros(4), constant=True)
+    for i in range(n):
+        init = gt[i] + (0 if i == 0 else rs.normal(0, 0.2, 4) * [1, 1, 1, 0.1])
+        pg.addSubmapNode(api.SubmapNodeConfig(i, init, set_constant=(i == 0)))
+        og.add_node(i, init, constant=(i == 0))
+    L = oracle.sqrt_information(info_odo); Lh = oracle.sqrt_information_ldlt(info_h)
+    for i in range(n - 1):
+        t, y = synth.relative_pose(gt[i], gt[i + 1])
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(i, i + 1, np.array([*t, y]), info_odo))
+        og.add_relative(i, i + 1, t, y, L)
+    for i in range(1, n):
+        pg.addAbsolutePoseConstraint(api.AbsolutePoseConstraintConfig(
+            0, i, np.array([0.0, 0.0, gt[i, 2] + 0.01, 0.0]), info_h,
+            allow_semi_definite_information_matrix=True))
+        og.add_relative(api.FRAME_NODE_ID_BASE, i, np.array([0.0, 0.0, gt[i, 2] + 0.01]), 0.0, Lh)
+    ok, cg_, gg, Hg = pg.evaluate()
+    ok, co, go_, Ho = og.eval()
+    # node order: the mirror sorts by id (submaps, then the frame node); the oracle has the frame first
+    perm = np.r_[np.arange(4, 4 * (n + 1)), np.arange(4)]
+    np.testing.assert_allclose(cg_, co, rtol=1e-12)
+    np.testing.assert_allclose(gg, go_[perm], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(Hg, Ho[np.ix_(perm, perm)], rtol=1e-10, atol=1e-9)
+    opts = dict(parameter_tolerance=1e-10, function_tolerance=1e-14, max_num_iterations=100)
+    pg.solver_options = ctx.solver_options(**opts)
+    s = pg.optimize()
+    rc, so = og.solve(oracle.solver_options(**opts))
+    xg = np.array([pg.getSubmapPoses()[i] for i in range(n)]); xo = og.poses()[1:]
+    assert np.abs(xg - xo).max() < 1e-7
+    assert np.abs(xg[1:, 2] - (gt[1:, 2] + 0.01)).max() < 0.02   # heights pulled to the measurements
+
+
 def test_solver_errors(ctx, oracle):
     from voxgraph_b200 import api
     pg = api.PoseGraph(ctx)
