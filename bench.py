@@ -351,11 +351,14 @@ def run_b200(args):
     ctx.profile_enable(False)
     # keep the GPU under the same evaluation load long enough for nvidia-smi (100 ms period) to
     # see it: the clocks line covers warm-up + the timed bracket + e2e + this sustained tail
-    t_tail = time.time()
-    while time.time() - t_tail < 0.6:
-        for _ in range(50):
-            ctx.graph_eval_async()
-        ctx.synchronize()
+    # (iteration count derived from the rank-reduced step time: every rank must issue the same
+    # number of evaluations, each one contains a collective)
+    n_tail = int(min(20000, max(50, 0.6 / max(ms_step * 1e-3, 1e-6))))
+    for k in range(n_tail):
+        ctx.graph_eval_async()
+        if k % 50 == 49:
+            ctx.synchronize()
+    ctx.synchronize()
     clocks = sampler.stop(t_load0, time.time()) if sampler else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed bracket + e2e + 0.6 s of the same evaluation loop"
@@ -495,6 +498,8 @@ def run_b200(args):
                                                          "reading_bricks_view": int(bricks_bytes)}}
         line.update(extras)
         _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
+    if world > 1:
+        dist.barrier()      # tear the peer mappings down together
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
