@@ -237,3 +237,45 @@ def test_transform_matches_yaw_rotation(oracle):
         np.testing.assert_allclose(trig[:4], [np.cos(read[3]), np.sin(read[3]),
                                               np.cos(read[3] - ref[3]), np.sin(read[3] - ref[3])],
                                    atol=1e-6)
+
+
+def test_random_field_matches_bruteforce_trilinear(oracle):
+    """Arbitrary (random) voxel data: the oracle's interpolated distance equals a brute-force
+    numpy trilinear interpolation with explicit corner weights -> pins corner/q ordering on data
+    that is not a low-order polynomial, including block-face crossings."""
+    rs = np.random.RandomState(9)
+    idx = np.array([[bx, by, bz] for bz in (-1, 0) for by in (-1, 0) for bx in (-1, 0)], np.int32)
+    d = rs.normal(size=(8, VPS ** 3)).astype(np.float32)
+    w = np.ones_like(d)
+    layer = oracle.Layer.from_blocks(VS, VPS, idx, d, w)
+    # dense lookup table of the same data
+    dense = np.zeros((32, 32, 32), np.float32)
+    for k, (bx, by, bz) in enumerate(idx):
+        blk = d[k].reshape(VPS, VPS, VPS)          # [z][y][x]
+        dense[(bx + 1) * 16:(bx + 2) * 16, (by + 1) * 16:(by + 2) * 16, (bz + 1) * 16:(bz + 2) * 16] = \
+            blk.transpose(2, 1, 0)
+    xyz = rs.uniform(-3.0, 3.0, (2000, 3)).astype(np.float32)
+    ok, r, jr, je = oracle.reg_evaluate(layer, xyz, np.zeros(2000, np.float32), np.ones(2000, np.float32),
+                                        np.zeros(4), np.zeros(4))
+    assert ok
+    p = xyz.astype(np.float64) / 0.2 - 0.5 + 16      # continuous voxel-centre coordinates in `dense`
+    i0 = np.floor(p).astype(int); f = p - i0
+    exp = np.zeros(2000); grad = np.zeros((2000, 3))
+    inside = np.all((i0 >= 0) & (i0 < 31), axis=1)
+    for cx in (0, 1):
+        for cy in (0, 1):
+            for cz in (0, 1):
+                wx = np.where(cx, f[:, 0], 1 - f[:, 0]); wy = np.where(cy, f[:, 1], 1 - f[:, 1])
+                wz = np.where(cz, f[:, 2], 1 - f[:, 2])
+                ii = np.clip(i0 + [cx, cy, cz], 0, 31)
+                val = dense[ii[:, 0], ii[:, 1], ii[:, 2]].astype(np.float64)
+                exp += wx * wy * wz * val
+                grad[:, 0] += (1 if cx else -1) * wy * wz * val / 0.2
+                grad[:, 1] += wx * (1 if cy else -1) * wz * val / 0.2
+                grad[:, 2] += wx * wy * (1 if cz else -1) * val / 0.2
+    has = np.abs(jr).sum(1) > 0
+    # points whose 8 corners lie inside the 2x2x2 blocks interpolate; the others have no correspondence
+    assert has[inside].mean() > 0.99 and inside.sum() > 1500
+    m = inside & has
+    np.testing.assert_allclose(-r[m], exp[m], atol=2e-5)
+    np.testing.assert_allclose(-jr[m, :3], grad[m], atol=5e-4)

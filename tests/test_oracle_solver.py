@@ -164,3 +164,45 @@ def test_full_graph_solve_reduces_error(oracle, small_scene):
     e0 = np.abs(sc.poses_init[:, :2] - sc.poses_gt[:, :2]).mean()
     e1 = np.abs(g.poses()[:, :2] - sc.poses_gt[:, :2]).mean()
     assert e1 < e0
+
+
+def test_lm_minimum_matches_scipy(oracle, pair_scene):
+    """Independent optimiser on the same residuals: scipy's trust-region least squares, driven by
+    the oracle's residual/Jacobian evaluations, reaches the minimum the oracle's Ceres-style LM
+    finds (config-1 problem: odometry edge + mirrored registration constraint)."""
+    from scipy.optimize import least_squares
+    sc = pair_scene
+    s0, s1 = sc.submaps
+    layers = [_layer_of(oracle, s) for s in sc.submaps]
+    L = oracle.sqrt_information(sc.odom_information)
+    (i, j, t_obs, yaw_obs) = sc.odometry[0]
+    x0 = sc.poses_init[1].copy(); ref = sc.poses_init[0].copy()
+
+    def fun(x):
+        r_rel, _, _ = oracle.relpose_evaluate(ref, x, t_obs, yaw_obs, L)
+        _, r01, _, _ = oracle.reg_evaluate(layers[1], s0.points_xyz, s0.points_distance, s0.points_weight,
+                                           ref, x, jacobians=False)
+        _, r10, _, _ = oracle.reg_evaluate(layers[0], s1.points_xyz, s1.points_distance, s1.points_weight,
+                                           x, ref, jacobians=False)
+        return np.concatenate([r_rel, r01, r10])
+
+    def jac(x):
+        _, _, jb = oracle.relpose_evaluate(ref, x, t_obs, yaw_obs, L)
+        _, _, _, je01 = oracle.reg_evaluate(layers[1], s0.points_xyz, s0.points_distance, s0.points_weight, ref, x)
+        _, _, jr10, _ = oracle.reg_evaluate(layers[0], s1.points_xyz, s1.points_distance, s1.points_weight, x, ref)
+        return np.vstack([jb, je01, jr10])
+
+    res = least_squares(fun, x0, jac=jac, method="trf", xtol=1e-12, ftol=1e-14, gtol=1e-12)
+    g = oracle.Graph()
+    g.add_node(0, ref, constant=True); g.add_node(1, x0, constant=False)
+    g.add_relative(0, 1, t_obs, yaw_obs, L)
+    g.add_registration(0, 1, layers[1], s0.points_xyz, s0.points_distance, s0.points_weight)
+    g.add_registration(1, 0, layers[0], s1.points_xyz, s1.points_distance, s1.points_weight)
+    rc, summ = g.solve(oracle.solver_options(parameter_tolerance=1e-12, function_tolerance=1e-14,
+                                             max_num_iterations=200))
+    assert rc == 0
+    x_lm = g.poses()[1]
+    # the cost is piecewise trilinear and evaluated in float32 (kinks + ~1e-7 noise): the two
+    # optimisers must agree on the minimum up to that noise floor
+    assert abs(summ.final_cost - res.cost) <= 1e-4 * max(res.cost, 1e-9)
+    assert np.abs(x_lm - res.x).max() < 1e-3
