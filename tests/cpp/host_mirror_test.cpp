@@ -64,6 +64,18 @@ int main() {
     try { RegistrationConstraintConfig bad; bad.first_submap_id = 0; bad.second_submap_id = 0; graph.addRegistrationConstraint(bad); }
     catch (const std::invalid_argument&) { threw = true; }
     if (!threw) { std::printf("self-constraint not rejected\n"); return 1; }
+    // height measurement through a reference-frame node (information only on z, LDLT sqrt)
+    ReferenceFrameNodeConfig frame; frame.reference_frame_id = 0;
+    graph.addReferenceFrameNode(frame);
+    AbsolutePoseConstraintConfig height; height.reference_frame_id = 0; height.submap_id = 1;
+    height.information_matrix = InformationMatrix{}; height.information_matrix[10] = 2500.0;
+    height.allow_semi_definite_information_matrix = true;
+    height.T_ref_submap = {0.0, 0.0, 0.0, 0.0};
+    graph.addAbsolutePoseConstraint(height);
+    const std::array<double, 16> Sh = SqrtInformation(height.information_matrix, true);
+    if (std::fabs(Sh[10] - 50.0) > 1e-12 || std::fabs(Sh[0]) + std::fabs(Sh[5]) + std::fabs(Sh[15]) > 0) {
+      std::printf("LDLT sqrt information wrong\n"); return 1;
+    }
     graph.solverOptions().parameter_tolerance = 1e-10;
     graph.optimize();
     const Pose4 p1 = graph.getSubmapPoses().at(1);

@@ -10,6 +10,7 @@
 // minkindr types are not available in this image, so plain arrays stand in for them.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -113,6 +114,72 @@ struct RelativePoseConstraintConfig {  // RelativePoseConstraint::Config
   SubmapID origin_submap_id = 0, destination_submap_id = 0;
   Pose4 T_origin_destination{};  // [t, yaw]
 };
+struct ReferenceFrameNodeConfig {  // ReferenceFrameNode::Config
+  bool set_constant = true;
+  Pose4 T_mission_node_initial{};
+  uint32_t reference_frame_id = 0;
+};
+struct AbsolutePoseConstraintConfig {  // AbsolutePoseConstraint::Config
+  InformationMatrix information_matrix = IdentityInformation();
+  bool allow_semi_definite_information_matrix = false;
+  uint32_t reference_frame_id = 0;
+  SubmapID submap_id = 0;
+  Pose4 T_ref_submap{};  // [t, yaw]
+};
+// reference-frame nodes share the C-ABI's uint32 node id space
+constexpr uint32_t kFrameNodeIdBase = 0x80000000u;
+
+// Constraint ctor (constraint.cpp:4-38): LLT lower factor, or Eigen's pivoted LDLT
+// (sqrt = P^T L sqrt(D) P) when semi-definite matrices are allowed. Throws like the CHECKs.
+inline std::array<double, 16> SqrtInformation(const InformationMatrix& info, bool allow_semi_definite) {
+  std::array<double, 16> S{};
+  if (!allow_semi_definite) {
+    for (int j = 0; j < 4; ++j) {
+      double d = info[5 * j];
+      for (int k = 0; k < j; ++k) d -= S[4 * j + k] * S[4 * j + k];
+      if (!(d > 0))
+        throw std::invalid_argument("The square root of the information matrix could not be computed, "
+                                    "make sure it is symmetric and positive definite");
+      S[5 * j] = std::sqrt(d);
+      for (int i = j + 1; i < 4; ++i) {
+        double v = info[4 * i + j];
+        for (int k = 0; k < j; ++k) v -= S[4 * i + k] * S[4 * j + k];
+        S[4 * i + j] = v / S[5 * j];
+      }
+    }
+    return S;
+  }
+  double A[4][4];
+  int perm[4] = {0, 1, 2, 3};
+  double scale = 0;
+  for (int i = 0; i < 4; ++i) {
+    scale = std::max(scale, std::fabs(info[5 * i]));
+    for (int j = 0; j < 4; ++j) A[i][j] = info[4 * i + j];
+  }
+  for (int k = 0; k < 4; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < 4; ++i)
+      if (std::fabs(A[i][i]) > std::fabs(A[piv][piv])) piv = i;
+    if (piv != k) {
+      for (int j = 0; j < 4; ++j) std::swap(A[k][j], A[piv][j]);
+      for (int i = 0; i < 4; ++i) std::swap(A[i][k], A[i][piv]);
+      std::swap(perm[k], perm[piv]);
+    }
+    const double d = A[k][k];
+    if (d < -1e-12 * (1.0 + scale)) throw std::invalid_argument("The information matrix must be positive semi-definite");
+    for (int i = k + 1; i < 4; ++i) A[i][k] = std::fabs(d) > 0 ? A[i][k] / d : 0.0;
+    for (int i = k + 1; i < 4; ++i)
+      for (int j = k + 1; j < 4; ++j) A[i][j] -= A[i][k] * d * A[j][k];
+    for (int j = k + 1; j < 4; ++j) A[k][j] = 0;
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j <= i; ++j) {
+      const double l = (i == j) ? 1.0 : A[i][j];
+      S[4 * perm[i] + perm[j]] = l * (A[j][j] > 0 ? std::sqrt(A[j][j]) : 0.0);
+    }
+  return S;
+}
+
 struct RegistrationConstraintConfig {  // RegistrationConstraint::Config
   InformationMatrix information_matrix = IdentityInformation();
   SubmapID first_submap_id = 0, second_submap_id = 0;
@@ -136,21 +203,32 @@ class PoseGraph {
 
   void addRelativePoseConstraint(const RelativePoseConstraintConfig& config) {
     // Constraint ctor (constraint.cpp:8-14): sqrt_information = LLT lower factor
-    std::array<double, 16> L{};
-    for (int j = 0; j < 4; ++j) {
-      double d = config.information_matrix[5 * j];
-      for (int k = 0; k < j; ++k) d -= L[4 * j + k] * L[4 * j + k];
-      if (!(d > 0))
-        throw std::invalid_argument("The square root of the information matrix could not be computed, "
-                                    "make sure it is symmetric and positive definite");
-      L[5 * j] = std::sqrt(d);
-      for (int i = j + 1; i < 4; ++i) {
-        double v = config.information_matrix[4 * i + j];
-        for (int k = 0; k < j; ++k) v -= L[4 * i + k] * L[4 * j + k];
-        L[4 * i + j] = v / L[5 * j];
-      }
-    }
-    relative_.push_back({config, L});
+    relative_.push_back({config, SqrtInformation(config.information_matrix, false)});
+    dirty_ = true;
+  }
+
+  void addReferenceFrameNode(const ReferenceFrameNodeConfig& config) {  // pose_graph.cpp:21-24
+    SubmapNodeConfig n;
+    n.submap_id = kFrameNodeIdBase + config.reference_frame_id;
+    n.set_constant = config.set_constant;
+    n.T_mission_node_initial = config.T_mission_node_initial;
+    nodes_[n.submap_id] = n;
+    dirty_ = true;
+  }
+  bool hasReferenceFrameNode(uint32_t frame_id) const { return nodes_.count(kFrameNodeIdBase + frame_id) != 0; }
+
+  // pose_graph.cpp:33-39 + absolute_pose_constraint.cpp:6-35 (height / GPS measurements)
+  void addAbsolutePoseConstraint(const AbsolutePoseConstraintConfig& config) {
+    if (!hasReferenceFrameNode(config.reference_frame_id))
+      throw std::invalid_argument("Graph contains no reference frame node " + std::to_string(config.reference_frame_id));
+    if (!hasSubmapNode(config.submap_id))
+      throw std::invalid_argument("Graph contains no node for submap " + std::to_string(config.submap_id));
+    RelativePoseConstraintConfig r;
+    r.information_matrix = config.information_matrix;
+    r.origin_submap_id = kFrameNodeIdBase + config.reference_frame_id;
+    r.destination_submap_id = config.submap_id;
+    r.T_origin_destination = config.T_ref_submap;
+    relative_.push_back({r, SqrtInformation(config.information_matrix, config.allow_semi_definite_information_matrix)});
     dirty_ = true;
   }
 
@@ -193,7 +271,8 @@ class PoseGraph {
 
   PoseMap getSubmapPoses() const {
     PoseMap m;
-    for (const auto& kv : nodes_) m.emplace(kv.first, kv.second.T_mission_node_initial);
+    for (const auto& kv : nodes_)
+      if (kv.first < kFrameNodeIdBase) m.emplace(kv.first, kv.second.T_mission_node_initial);
     return m;
   }
   const std::vector<SolverSummary>& getSolverSummaries() const { return solver_summaries_; }
