@@ -363,9 +363,10 @@ extern "C" int vgx_submap_finish(vgx_ctx* c, uint32_t id) {
   VgxSubmap* s = c->find(id);
   if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_finish: unknown submap");
   VGX_CUDA(c, cudaSetDevice(c->device));
-  const size_t nvox = (size_t)s->cap_blocks * s->vox_per_block;
-  if (!s->d_view) VGX_CUDA(c, cudaMalloc(&s->d_view, sizeof(float) * 8 * nvox));
+  // the layer is frozen from here on: the view only needs the blocks that exist, not the
+  // integration capacity (128 KiB per brick)
   const size_t used = (size_t)s->n_blocks * s->vox_per_block;
+  if (!s->d_view) VGX_CUDA(c, cudaMalloc(&s->d_view, sizeof(float) * 8 * (used > 0 ? used : 1)));
   if (used > 0) {
     int sh = 0;
     while ((1 << sh) < s->vps) sh++;
