@@ -133,6 +133,10 @@ def lib():
     L.vgo_graph_eval.argtypes = [vp, C.c_int, C.c_int, f64p, f64p, f64p]
     L.vgo_graph_registration_costs.argtypes = [vp, f64p]
     L.vgo_graph_solve.argtypes = [vp, C.POINTER(SolverOptions), C.POINTER(SolverSummary)]
+    L.vgo_find_relevant_voxels.argtypes = [vp, C.c_double, C.c_double, f32p, f32p, f32p, C.c_int]
+    L.vgo_surface_obb.argtypes = [vp, C.c_double, C.c_double, f32p, f32p]
+    L.vgo_aabb_from_obb_and_pose.argtypes = [f32p, f32p, f32p, f32p, f32p]
+    L.vgo_submaps_overlap.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_float, vp]
     L.vgo_tsdf_config_default.argtypes = [C.POINTER(TsdfConfig)]
     L.vgo_tsdf_integrate.argtypes = [vp, C.POINTER(TsdfConfig), f32p, C.c_int, f32p,
                                      C.POINTER(TsdfStats)]
@@ -394,6 +398,41 @@ class Graph:
         s = SolverSummary()
         rc = lib().vgo_graph_solve(self._h, C.byref(o), C.byref(s))
         return rc, s
+
+
+def find_relevant_voxels(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):
+    """findRelevantVoxelIndices -> (xyz (n,3), distance (n,), weight (n,))."""
+    n = lib().vgo_find_relevant_voxels(layer._h, float(min_voxel_weight), float(max_voxel_distance),
+                                       None, None, None, 0)
+    xyz = np.zeros((n, 3), np.float32); d = np.zeros(n, np.float32); w = np.zeros(n, np.float32)
+    lib().vgo_find_relevant_voxels(layer._h, float(min_voxel_weight), float(max_voxel_distance),
+                                   _p(xyz, C.c_float), _p(d, C.c_float), _p(w, C.c_float), n)
+    return xyz, d, w
+
+
+def surface_obb(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):
+    mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
+    ok = lib().vgo_surface_obb(layer._h, float(min_voxel_weight), float(max_voxel_distance),
+                               _p(mn, C.c_float), _p(mx, C.c_float))
+    return bool(ok), mn, mx
+
+
+def aabb_from_obb_and_pose(obb_min, obb_max, pose_T):
+    a = f32(obb_min); b = f32(obb_max); T = f32(pose_T)
+    mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
+    lib().vgo_aabb_from_obb_and_pose(_p(a, C.c_float), _p(b, C.c_float), _p(T, C.c_float),
+                                     _p(mn, C.c_float), _p(mx, C.c_float))
+    return mn, mx
+
+
+def submaps_overlap(aabb, other_aabb, pose_T, other_pose_T, isosurface_blocks, block_size, other_layer):
+    blk = np.ascontiguousarray(isosurface_blocks, np.int32).reshape(-1, 3)
+    a0, a1 = f32(aabb[0]), f32(aabb[1]); b0, b1 = f32(other_aabb[0]), f32(other_aabb[1])
+    T = f32(pose_T); To = f32(other_pose_T)
+    return bool(lib().vgo_submaps_overlap(_p(a0, C.c_float), _p(a1, C.c_float), _p(b0, C.c_float),
+                                          _p(b1, C.c_float), _p(T, C.c_float), _p(To, C.c_float),
+                                          _p(blk, C.c_int32), blk.shape[0], float(block_size),
+                                          other_layer._h))
 
 
 def tsdf_config(**kw):

@@ -1021,6 +1021,102 @@ done:
 }
 
 /* ========================================================================= */
+/* registration-voxel extraction, OBB/AABB, overlap test    */
+/* ========================================================================= */
+int vgo_find_relevant_voxels(const vgo_layer* l, double min_w, double max_d, float* xyz,
+                             float* distance, float* weight, int max_n) {
+  int n = 0;
+  const int vps = l->vps;
+  for (int b = 0; b < l->n_blocks; ++b) {
+    const int32_t* bi = l->idx + 3 * b;
+    const float origin[3] = {(float)bi[0] * l->block_size, (float)bi[1] * l->block_size,
+                             (float)bi[2] * l->block_size};
+    for (int lin = 0; lin < l->vox_per_block; ++lin) {
+      const size_t o = (size_t)b * l->vox_per_block + lin;
+      /* cpp:177-178 (double comparison of float members) */
+      if ((double)l->weight[o] > min_w && fabs((double)l->distance[o]) < max_d) {
+        if (n < max_n) {
+          /* Block::computeCoordinatesFromLinearIndex: origin + (voxel_index + 0.5) * voxel_size */
+          const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
+          xyz[3 * n + 0] = origin[0] + ((float)vx + 0.5f) * l->voxel_size;
+          xyz[3 * n + 1] = origin[1] + ((float)vy + 0.5f) * l->voxel_size;
+          xyz[3 * n + 2] = origin[2] + ((float)vz + 0.5f) * l->voxel_size;
+          distance[n] = l->distance[o];
+          weight[n] = l->weight[o];
+        }
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+int vgo_surface_obb(const vgo_layer* l, double min_w, double max_d, float mn[3], float mx[3]) {
+  const int vps = l->vps;
+  const float half = 0.5f * l->voxel_size;
+  int any = 0;
+  for (int a = 0; a < 3; ++a) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+  for (int b = 0; b < l->n_blocks; ++b) {
+    const int32_t* bi = l->idx + 3 * b;
+    const float origin[3] = {(float)bi[0] * l->block_size, (float)bi[1] * l->block_size,
+                             (float)bi[2] * l->block_size};
+    for (int lin = 0; lin < l->vox_per_block; ++lin) {
+      const size_t o = (size_t)b * l->vox_per_block + lin;
+      if ((double)l->weight[o] > min_w && fabs((double)l->distance[o]) < max_d) {
+        const int v[3] = {lin % vps, (lin / vps) % vps, lin / (vps * vps)};
+        for (int a = 0; a < 3; ++a) {
+          const float c = origin[a] + ((float)v[a] + 0.5f) * l->voxel_size;
+          if (c - half < mn[a]) mn[a] = c - half;
+          if (c + half > mx[a]) mx[a] = c + half;
+        }
+        any = 1;
+      }
+    }
+  }
+  return any;
+}
+
+void vgo_aabb_from_obb_and_pose(const float omin[3], const float omax[3], const float pose[7],
+                                float amin[3], float amax[3]) {
+  for (int a = 0; a < 3; ++a) { amin[a] = INFINITY; amax[a] = -INFINITY; }
+  for (unsigned i = 0; i < 8; ++i) {
+    /* getCornerCoordinates: bit set -> min, clear -> max */
+    const float corner[3] = {(i & 1) ? omin[0] : omax[0], (i & 2) ? omin[1] : omax[1],
+                             (i & 4) ? omin[2] : omax[2]};
+    float m[3];
+    vgo_T_transform(pose, corner, m);
+    for (int a = 0; a < 3; ++a) {
+      if (m[a] < amin[a]) amin[a] = m[a];
+      if (m[a] > amax[a]) amax[a] = m[a];
+    }
+  }
+}
+
+int vgo_submaps_overlap(const float amin[3], const float amax[3], const float bmin[3],
+                        const float bmax[3], const float pose_current[7], const float pose_other[7],
+                        const int32_t* blocks, int n, float block_size, const vgo_layer* other) {
+  /* cpp:251-256 */
+  for (int a = 0; a < 3; ++a)
+    if (amax[a] < bmin[a] || amin[a] > bmax[a]) return 0;
+  /* cpp:261-262: T_other_submap__current_submap = other.getPose().inverse() * getPose() */
+  float inv[7], T[7];
+  vgo_T_inverse(pose_other, inv);
+  vgo_T_compose(inv, pose_current, T);
+  for (int i = 0; i < n; ++i) {
+    /* getCenterPointFromGridIndex(block_index, block_size) */
+    const float c[3] = {((float)blocks[3 * i] + 0.5f) * block_size,
+                        ((float)blocks[3 * i + 1] + 0.5f) * block_size,
+                        ((float)blocks[3 * i + 2] + 0.5f) * block_size};
+    float p[3];
+    vgo_T_transform(T, c, p);
+    int32_t ob[3];
+    vgo_grid_index_from_point(p, other->block_size_inv, ob);
+    if (vgo_layer_find_block(other, ob) >= 0) return 1;
+  }
+  return 0;
+}
+
+/* ========================================================================= */
 /* TSDF integration (A.4)                                                    */
 /* ========================================================================= */
 void vgo_tsdf_config_default(vgo_tsdf_config* c) {

@@ -180,6 +180,33 @@ void vgo_graph_registration_costs(vgo_graph* g, double* per_constraint_sq_sum);
 int vgo_graph_solve(vgo_graph* g, const vgo_solver_options* opts, vgo_solver_summary* summary);
 
 /* ------------------------------------------------------------------------- */
+/* "Next" rows of SURVEY §8f, restated ahead of their GPU versions            */
+/* (src/frontend/submap_collection/voxgraph_submap.cpp, bounding_box.cpp)    */
+/* ------------------------------------------------------------------------- */
+/* VoxgraphSubmap::findRelevantVoxelIndices (voxgraph_submap.cpp:144-201), TSDF-distance branch:
+ * every voxel with weight > min_voxel_weight and |distance| < max_voxel_distance becomes a
+ * RegistrationPoint {voxel centre, distance, weight}, blocks in allocation order, voxels in
+ * linear order. Writes at most max_n entries, returns the total count. */
+int vgo_find_relevant_voxels(const vgo_layer* layer, double min_voxel_weight,
+                             double max_voxel_distance, float* xyz, float* distance,
+                             float* weight, int max_n);
+/* VoxgraphSubmap::getSubmapFrameSurfaceObb (voxgraph_submap.cpp:280-324). Returns 0 when no
+ * voxel qualifies (box stays +-inf). */
+int vgo_surface_obb(const vgo_layer* layer, double min_voxel_weight, double max_voxel_distance,
+                    float obb_min[3], float obb_max[3]);
+/* BoundingBox::getAabbFromObbAndPose (bounding_box.cpp:28-42); pose = [qw qx qy qz tx ty tz]. */
+void vgo_aabb_from_obb_and_pose(const float obb_min[3], const float obb_max[3], const float pose[7],
+                                float aabb_min[3], float aabb_max[3]);
+/* VoxgraphSubmap::overlapsWith (voxgraph_submap.cpp:245-278): mission-frame surface AABB
+ * rejection, then "any isosurface block centre of the current submap lands in an allocated block
+ * of the other". isosurface_blocks: n x 3 block indices of the current submap. */
+int vgo_submaps_overlap(const float aabb_min[3], const float aabb_max[3],
+                        const float other_aabb_min[3], const float other_aabb_max[3],
+                        const float pose_current[7], const float pose_other[7],
+                        const int32_t* isosurface_blocks, int n, float block_size_current,
+                        const vgo_layer* other_layer);
+
+/* ------------------------------------------------------------------------- */
 /* TSDF integration (voxblox tsdf_integrator.cc / integrator_utils, A.4)      */
 /* ------------------------------------------------------------------------- */
 typedef struct vgo_tsdf_config {
