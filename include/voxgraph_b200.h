@@ -74,6 +74,9 @@ int vgx_submap_create(vgx_ctx* ctx, uint32_t submap_id, float voxel_size, int vo
 int vgx_submap_finish(vgx_ctx* ctx, uint32_t submap_id);
 int vgx_submap_free(vgx_ctx* ctx, uint32_t submap_id);
 int vgx_submap_block_count(vgx_ctx* ctx, uint32_t submap_id, int* n_blocks);
+/* Layer geometry and state (any output may be NULL). */
+int vgx_submap_info(vgx_ctx* ctx, uint32_t submap_id, float* voxel_size, int* voxels_per_side,
+                    int* n_blocks, int* finished);
 /* Copies blocks back in allocation order (parity checks / saving). */
 int vgx_submap_download(vgx_ctx* ctx, uint32_t submap_id, int max_blocks, int32_t* block_idx,
                         float* distance, float* weight, int* n_blocks);
@@ -125,7 +128,14 @@ int vgx_tsdf_integrate(vgx_ctx* ctx, uint32_t submap_id, const float T_G_C[7], i
 typedef struct vgx_reg_config {           /* RegistrationCostFunction::Config (h:17-41) */
   int registration_point_type;            /* VGX_POINTS_* ; default isosurface */
   double no_correspondence_cost;          /* 0 */
-  float sampling_ratio;                   /* -1 (only the deterministic mode is supported) */
+  float sampling_ratio;                   /* -1: every registration point, in order (cpp:115-117).
+                                             Otherwise (voxgraph_mapper.yaml:34 uses 0.05):
+                                             num_residuals = int(ratio * K) points are drawn with
+                                             probability proportional to their weight from the
+                                             reference submap's WeightedSampler (a default-seeded
+                                             std::mt19937 per submap and point type,
+                                             weighted_sampler_inl.h:19-28) and their weight is
+                                             forced to 1 (cpp:118-122). */
 } vgx_reg_config;
 void vgx_reg_config_default(vgx_reg_config* cfg);
 
@@ -134,11 +144,18 @@ int vgx_reg_num_residuals(vgx_ctx* ctx, uint32_t reference_submap_id, const vgx_
                           int* num_residuals);
 /* Evaluate(parameters, residuals, jacobians): Ceres layout, residuals[K] and two K x 4
  * row-major Jacobian blocks (either may be NULL). Returns VGX_OK, or VGX_ZERO_WEIGHT
- * where Evaluate returns false. */
+ * where Evaluate returns false.  In sampling mode every call draws a fresh sample from the
+ * reference submap's generator, exactly as every Evaluate does in the reference. */
 int vgx_reg_eval_emit(vgx_ctx* ctx, uint32_t reference_submap_id, uint32_t reading_submap_id,
                       const vgx_reg_config* cfg, const double reference_pose[4],
                       const double reading_pose[4], double* residuals, double* jac_reference,
                       double* jac_reading);
+
+/* WeightedSampler::getRandomItem (weighted_sampler_inl.h:19-28) n times on the submap's
+ * generator: writes the n drawn point indices and advances the generator (inspection / parity
+ * tests; the same routine feeds the sampling mode of b1 and b2). */
+int vgx_submap_draw_samples(vgx_ctx* ctx, uint32_t submap_id, int point_type, int n,
+                            int32_t* indices);
 
 /* ------------------------------------------------------------------ b2: pose graph */
 /* addSubmapNode for every node (replaces the node set). xyzyaw: n x 4 [x,y,z,yaw]. */
@@ -155,6 +172,21 @@ int vgx_graph_set_relative_edges(vgx_ctx* ctx, int m, const uint32_t* ids_a, con
  * (pose_graph.cpp:63-71). Replaces the previous list (resetRegistrationConstraints). */
 int vgx_graph_set_registration_constraints(vgx_ctx* ctx, int p, const uint32_t* reference_ids,
                                            const uint32_t* reading_ids, const vgx_reg_config* cfg);
+/* Same with one config per residual block (the reference keeps a Config per constraint,
+ * registration_constraint.h:15-21). */
+int vgx_graph_set_registration_constraints_v(vgx_ctx* ctx, int p, const uint32_t* reference_ids,
+                                             const uint32_t* reading_ids,
+                                             const vgx_reg_config* cfgs /* p entries */);
+/* Sampling mode inside the fused evaluation: the reference re-draws on every Evaluate, i.e. the
+ * cost Ceres compares between two LM iterations is stochastic.  The fused path draws ONCE per
+ * constraint when the constraint list is (re)built - PoseGraphInterface resets and re-adds the
+ * registration constraints before every optimize() (pose_graph_interface.cpp:149-175), so every
+ * solve gets a fresh draw from the submap's generator - and keeps it for all evaluations of
+ * that solve.  Every rank draws for every constraint, so the streams stay identical across
+ * ranks.  get: the indices in use (n = num_residuals of that block); set: replace them
+ * (parity tests against an oracle fed with the same list). constraint = index in the list. */
+int vgx_graph_get_sample_indices(vgx_ctx* ctx, int constraint, int max_n, int32_t* indices, int* n);
+int vgx_graph_set_sample_indices(vgx_ctx* ctx, int constraint, int n, const int32_t* indices);
 int vgx_graph_num_registration_residuals(vgx_ctx* ctx, int64_t* local, int64_t* global);
 
 /* Whole-problem evaluation at the current poses, fused on the device: cost = 1/2 sum r^2,

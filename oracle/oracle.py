@@ -27,6 +27,54 @@ def build(force=False):
     return _LIB_PATH
 
 
+_REF_SAMPLER_PATH = os.path.join(_HERE, "_ref", "libvgref_sampler.so")
+_ref_sampler = None
+
+
+def ref_sampler_lib():
+    """oracle/_ref/libvgref_sampler.so: the REFERENCE's own WeightedSampler template compiled from
+    /root/reference (oracle/ref_sampler_shim.cpp + Makefile target `ref`).  Returns None when it has
+    not been built (no /root/reference and no prebuilt file)."""
+    global _ref_sampler
+    if _ref_sampler is None:
+        if not os.path.exists(_REF_SAMPLER_PATH):
+            if os.path.isdir("/root/reference/voxgraph/include"):
+                subprocess.run(["make", "-C", _HERE, "ref"], check=False, stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT)
+            if not os.path.exists(_REF_SAMPLER_PATH):
+                return None
+        L = C.CDLL(_REF_SAMPLER_PATH)
+        L.vgref_sampler_create.restype = C.c_void_p
+        L.vgref_sampler_create.argtypes = [C.POINTER(C.c_float), C.c_int]
+        L.vgref_sampler_destroy.argtypes = [C.c_void_p]
+        L.vgref_sampler_draw.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+        _ref_sampler = L
+    return _ref_sampler
+
+
+class RefWeightedSampler:
+    """The reference's voxgraph::WeightedSampler (compiled, oracle/_ref)."""
+
+    def __init__(self, weights):
+        L = ref_sampler_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libvgref_sampler.so is not built")
+        w = np.ascontiguousarray(weights, np.float32)
+        self._L = L
+        self._h = L.vgref_sampler_create(_p(w, C.c_float), len(w))
+
+    def draw(self, count):
+        idx = np.zeros(count, np.int32)
+        self._L.vgref_sampler_draw(self._h, int(count), _p(idx, C.c_int32))
+        return idx
+
+    def __del__(self):
+        try:
+            self._L.vgref_sampler_destroy(self._h)
+        except Exception:
+            pass
+
+
 class SolverOptions(C.Structure):
     _fields_ = [("max_num_iterations", C.c_int),
                 ("parameter_tolerance", C.c_double),
@@ -137,6 +185,12 @@ def lib():
     L.vgo_surface_obb.argtypes = [vp, C.c_double, C.c_double, f32p, f32p]
     L.vgo_aabb_from_obb_and_pose.argtypes = [f32p, f32p, f32p, f32p, f32p]
     L.vgo_submaps_overlap.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_float, vp]
+    L.vgo_sampler_init.argtypes = [vp]
+    L.vgo_sampler_next_u32.argtypes = [vp]
+    L.vgo_sampler_next_u32.restype = C.c_uint32
+    L.vgo_sampler_canonical.argtypes = [vp]
+    L.vgo_sampler_canonical.restype = C.c_double
+    L.vgo_sampler_draw.argtypes = [vp, f64p, C.c_int, C.c_int, i32p]
     L.vgo_tsdf_config_default.argtypes = [C.POINTER(TsdfConfig)]
     L.vgo_tsdf_integrate.argtypes = [vp, C.POINTER(TsdfConfig), f32p, C.c_int, f32p,
                                      C.POINTER(TsdfStats)]
@@ -398,6 +452,47 @@ class Graph:
         s = SolverSummary()
         rc = lib().vgo_graph_solve(self._h, C.byref(o), C.byref(s))
         return rc, s
+
+
+class WeightedSampler:
+    """WeightedSampler<RegistrationPoint> (weighted_sampler.h:10-37): cumulative double weights +
+    a default-seeded mt19937; draw(count) = getRandomItem x count -> item indices."""
+
+    def __init__(self, weights):
+        w = np.asarray(weights, np.float32)
+        self.cumulative = np.cumsum(w.astype(np.float64))   # addItem: sequential double sums
+        self._state = (C.c_uint32 * 625)()
+        lib().vgo_sampler_init(C.cast(self._state, C.c_void_p))
+
+    def next_u32(self):
+        return int(lib().vgo_sampler_next_u32(C.cast(self._state, C.c_void_p)))
+
+    def canonical(self):
+        return float(lib().vgo_sampler_canonical(C.cast(self._state, C.c_void_p)))
+
+    def draw(self, count):
+        idx = np.zeros(count, np.int32)
+        cum = np.ascontiguousarray(self.cumulative)
+        lib().vgo_sampler_draw(C.cast(self._state, C.c_void_p), _p(cum, C.c_double), len(cum),
+                               int(count), _p(idx, C.c_int32))
+        return idx
+
+
+def sampled_num_residuals(sampling_ratio, n_points):
+    """registration_cost_function.cpp:45-55: int(float ratio * size())."""
+    if sampling_ratio == -1:
+        return int(n_points)
+    return int(np.float32(sampling_ratio) * np.float32(n_points))
+
+
+def reg_evaluate_sampled(layer, xyz, distance, indices, ref_pose, read_pose,
+                         no_correspondence_cost=0.0, jacobians=True):
+    """Evaluate in sampling mode (cpp:118-122) for a given draw: residual j uses point
+    indices[j] with its weight forced to 1."""
+    idx = np.asarray(indices, np.int64)
+    return reg_evaluate(layer, np.asarray(xyz, np.float32)[idx], np.asarray(distance, np.float32)[idx],
+                        np.ones(len(idx), np.float32), ref_pose, read_pose,
+                        no_correspondence_cost=no_correspondence_cost, jacobians=jacobians)
 
 
 def find_relevant_voxels(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):

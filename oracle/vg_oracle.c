@@ -1117,6 +1117,60 @@ int vgo_submaps_overlap(const float amin[3], const float amax[3], const float bm
 }
 
 /* ========================================================================= */
+/* WeightedSampler::getRandomItem (weighted_sampler_inl.h:19-28)             */
+/* ========================================================================= */
+void vgo_sampler_init(vgo_sampler* s) {
+  /* std::mersenne_twister_engine<uint32, 32, 624, 397, 31, 0x9908b0df, 11, 0xffffffff, 7,
+   * 0x9d2c5680, 15, 0xefc60000, 18, 1812433253>, default_seed = 5489 */
+  s->mt[0] = 5489u;
+  for (int i = 1; i < 624; ++i)
+    s->mt[i] = 1812433253u * (s->mt[i - 1] ^ (s->mt[i - 1] >> 30)) + (uint32_t)i;
+  s->idx = 624;
+}
+
+uint32_t vgo_sampler_next_u32(vgo_sampler* s) {
+  if (s->idx >= 624) {
+    for (int i = 0; i < 624; ++i) {
+      const uint32_t y = (s->mt[i] & 0x80000000u) | (s->mt[(i + 1) % 624] & 0x7fffffffu);
+      uint32_t v = s->mt[(i + 397) % 624] ^ (y >> 1);
+      if (y & 1u) v ^= 0x9908b0dfu;
+      s->mt[i] = v;
+    }
+    s->idx = 0;
+  }
+  uint32_t y = s->mt[s->idx++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+double vgo_sampler_canonical(vgo_sampler* s) {
+  /* std::generate_canonical<double, 53>: k = ceil(53 / 32) = 2 draws, sum in double,
+   * divided by 2^64; a result of 1.0 is replaced by nextafter(1, 0) */
+  const double g1 = (double)vgo_sampler_next_u32(s);
+  const double g2 = (double)vgo_sampler_next_u32(s);
+  double r = (g1 + g2 * 4294967296.0) / 18446744073709551616.0;
+  if (r >= 1.0) r = nextafter(1.0, 0.0);
+  return r;
+}
+
+void vgo_sampler_draw(vgo_sampler* s, const double* cum, int n, int count, int32_t* idx) {
+  for (int i = 0; i < count; ++i) {
+    const double t = vgo_sampler_canonical(s) * cum[n - 1];
+    /* std::upper_bound: first element > t */
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (cum[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= n) lo = n - 1; /* the reference would read one past the end here */
+    idx[i] = lo;
+  }
+}
+
+/* ========================================================================= */
 /* TSDF integration (A.4)                                                    */
 /* ========================================================================= */
 void vgo_tsdf_config_default(vgo_tsdf_config* c) {

@@ -207,6 +207,24 @@ int vgo_submaps_overlap(const float aabb_min[3], const float aabb_max[3],
                         const vgo_layer* other_layer);
 
 /* ------------------------------------------------------------------------- */
+/* WeightedSampler<RegistrationPoint>::getRandomItem                          */
+/* (include/voxgraph/frontend/submap_collection/weighted_sampler_inl.h:19-28, */
+/*  weighted_sampler.h:34-36): std::mt19937 (default seed 5489) through        */
+/*  std::uniform_real_distribution<double>(0, 1) = generate_canonical<double,  */
+/*  53> = two 32-bit draws, then upper_bound over the cumulative weights.      */
+/* ------------------------------------------------------------------------- */
+typedef struct vgo_sampler {
+  uint32_t mt[624];
+  int idx;
+} vgo_sampler;
+void vgo_sampler_init(vgo_sampler* s);                 /* default-constructed std::mt19937 */
+uint32_t vgo_sampler_next_u32(vgo_sampler* s);         /* std::mt19937::operator() */
+double vgo_sampler_canonical(vgo_sampler* s);          /* uniform_real_distribution<double>(0,1)(gen) */
+/* cumulative = WeightedSampler::cumulative_item_weights_ (double prefix sums of the float
+ * weights, addItem inl.h:6-17); writes `count` drawn indices. */
+void vgo_sampler_draw(vgo_sampler* s, const double* cumulative, int n, int count, int32_t* idx);
+
+/* ------------------------------------------------------------------------- */
 /* TSDF integration (voxblox tsdf_integrator.cc / integrator_utils, A.4)      */
 /* ------------------------------------------------------------------------- */
 typedef struct vgo_tsdf_config {

@@ -171,7 +171,7 @@ def test_emit_zero_weight_and_errors(ctx, oracle):
     with pytest.raises(api.VgxError):
         ctx.reg_eval_emit(200, 200, np.zeros(4), np.zeros(4))       # submap against itself
     with pytest.raises(api.VgxError):
-        ctx.reg_eval_emit(201, 200, np.zeros(4), np.zeros(4), ctx.reg_config(sampling_ratio=0.05))
+        ctx.reg_eval_emit(201, 200, np.zeros(4), np.zeros(4), ctx.reg_config(sampling_ratio=-0.5))
 
 
 def _build_graphs(ctx, oracle, sc, api):
@@ -243,3 +243,95 @@ def test_device_pose_setup_matches_host(ctx, oracle, pair_scene):
     assert abs(cost - tot) <= 1e-6 * tot
     assert np.abs(H - Hx).max() <= 1e-6 * np.abs(Hx).max()
     assert np.abs(g - gx).max() <= 1e-6 * np.abs(gx).max()
+
+
+# --------------------------------------------------------------------------- sampling mode
+def test_draw_samples_match_reference_golden(ctx):
+    """vgx_submap_draw_samples == voxgraph::WeightedSampler::getRandomItem of the reference itself
+    (golden generated from the compiled reference header, tests/golden/make_sampler_golden.py)."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "weighted_sampler.json")))["cases"]
+    idx, d, w = synth.plane_layer_blocks([0, 0, 1.0], 0.0, VS, VPS, ((0, 0), (0, 0), (0, 0)))
+    for k, case in enumerate(cases):
+        wts = np.array(case["weights"], np.float32)
+        sid = 300 + k
+        ctx.submap_upload(sid, VS, VPS, idx, d, w)
+        n = len(wts)
+        ctx.submap_upload_points(sid, 1, np.zeros((n, 3), np.float32), np.zeros(n, np.float32), wts)
+        assert ctx.submap_draw_samples(sid, 1, 64).tolist() == case["draw_0_64"]
+        assert ctx.submap_draw_samples(sid, 1, 64).tolist() == case["draw_64_128"]
+
+
+def test_emit_sampling_mode_bit_exact(ctx, oracle, pair_scene):
+    """sampling_ratio = 0.2 (registration_test_bench.yaml:27) and 0.05 (voxgraph_mapper.yaml:34):
+    every Evaluate draws int(ratio*K) points from the reference submap's generator, weight 1."""
+    for s in pair_scene.submaps:
+        ctx.upload_synth_submap(s)      # fresh upload = fresh default-seeded generator
+    s0, s1 = pair_scene.submaps
+    layer = _olayer(oracle, s1)
+    sampler = oracle.WeightedSampler(s0.points_weight)
+    ref, read = pair_scene.poses_init[0], pair_scene.poses_init[1]
+    for ratio in (0.2, 0.05, 0.2):
+        cfg = ctx.reg_config(sampling_ratio=ratio)
+        K = oracle.sampled_num_residuals(ratio, len(s0.points_weight))
+        assert ctx.reg_num_residuals(0, cfg) == K
+        idx = sampler.draw(K)           # the oracle's generator advances in lock-step
+        ok_o, r_o, jr_o, je_o = oracle.reg_evaluate_sampled(layer, s0.points_xyz, s0.points_distance,
+                                                            idx, ref, read)
+        ok_g, r_g, jr_g, je_g = ctx.reg_eval_emit(0, 1, ref, read, cfg)
+        assert ok_o and ok_g and len(r_g) == K
+        assert _bit_equal(r_g, r_o) and _bit_equal(jr_g, jr_o) and _bit_equal(je_g, je_o)
+
+
+def test_graph_sampling_mode_matches_oracle(ctx, oracle, small_scene):
+    """The reference's production configuration (sampling_ratio 0.05) through the fused path: the
+    indices the library drew (one draw per constraint-list build) feed the oracle."""
+    from voxgraph_b200 import api
+    sc = small_scene
+    for s in sc.submaps:
+        ctx.upload_synth_submap(s)
+    pg = api.PoseGraph(ctx)
+    og = oracle.Graph()
+    layers = [_olayer(oracle, s) for s in sc.submaps]
+    for i, s in enumerate(sc.submaps):
+        pg.addSubmapNode(api.SubmapNodeConfig(i, sc.poses_init[i], set_constant=(i == 0)))
+        og.add_node(i, sc.poses_init[i], constant=(i == 0))
+    L = oracle.sqrt_information(sc.odom_information)
+    for (i, j, t, y) in sc.odometry:
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(
+            i, j, np.array([t[0], t[1], t[2], y]), sc.odom_information))
+        og.add_relative(i, j, t, y, L)
+    ratios = [0.05, 0.5]
+    for k, (i, j) in enumerate(sc.pairs):
+        pg.addRegistrationConstraint(api.RegistrationConstraintConfig(i, j, sampling_ratio=ratios[k % 2]))
+    pg._sync()
+    samplers = {i: oracle.WeightedSampler(s.points_weight) for i, s in enumerate(sc.submaps)}
+    keep = []
+    for k, (a, b) in enumerate(pg.registration_blocks):
+        ratio = ratios[(k // 2) % 2]
+        K = oracle.sampled_num_residuals(ratio, len(sc.submaps[a].points_weight))
+        idx = ctx.graph_get_sample_indices(k, K)
+        assert len(idx) == K
+        # the library's draw is the reference sampler's stream of submap a, in list order
+        assert np.array_equal(idx, samplers[a].draw(K))
+        sa = sc.submaps[a]
+        xyz = np.ascontiguousarray(sa.points_xyz[idx]); dd = np.ascontiguousarray(sa.points_distance[idx])
+        ww = np.ones(K, np.float32)
+        keep.append((xyz, dd, ww))
+        og.add_registration(a, b, layers[b], xyz, dd, ww)
+    ok_g, cost_g, g_g, H_g = pg.evaluate()
+    ok_o, cost_o, g_o, H_o = og.eval(num_threads=2)
+    assert ok_g and ok_o
+    assert abs(cost_g - cost_o) <= 1e-9 * abs(cost_o)
+    assert np.abs(g_g - g_o).max() <= 1e-7 * np.abs(g_o).max()
+    assert np.abs(H_g - H_o).max() <= 1e-7 * np.abs(H_o).max()
+    # the sample is frozen within a solve: evaluating again gives the identical numbers
+    ok_g, cost_g2, g_g2, H_g2 = pg.evaluate()
+    assert cost_g2 == cost_g and np.array_equal(H_g2, H_g)
+    # explicit index list (vgx_graph_set_sample_indices)
+    K0 = oracle.sampled_num_residuals(ratios[0], len(sc.submaps[pg.registration_blocks[0][0]].points_weight))
+    ctx.graph_set_sample_indices(0, np.arange(K0, dtype=np.int32))
+    assert np.array_equal(ctx.graph_get_sample_indices(0, K0), np.arange(K0))
+    summ = pg.optimize()
+    assert summ.final_cost <= summ.initial_cost

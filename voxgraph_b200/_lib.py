@@ -87,6 +87,8 @@ EXPORTS = [
     "vgx_solver_options_default", "vgx_graph_solve", "vgx_shard_constraints", "vgx_comm_unique_id",
     "vgx_comm_init",
     "vgx_comm_destroy", "vgx_comm_p2p_export", "vgx_comm_p2p_import",
+    "vgx_submap_info", "vgx_submap_draw_samples", "vgx_graph_set_registration_constraints_v",
+    "vgx_graph_get_sample_indices", "vgx_graph_set_sample_indices",
 ]
 
 _lib = None
@@ -140,6 +142,11 @@ def load():
     L.vgx_graph_get_poses.argtypes = [vp, pd]
     L.vgx_graph_set_relative_edges.argtypes = [vp, i32, pu32, pu32, pd, pd]
     L.vgx_graph_set_registration_constraints.argtypes = [vp, i32, pu32, pu32, C.POINTER(RegConfig)]
+    L.vgx_graph_set_registration_constraints_v.argtypes = [vp, i32, pu32, pu32, C.POINTER(RegConfig)]
+    L.vgx_graph_get_sample_indices.argtypes = [vp, i32, i32, pi32, C.POINTER(i32)]
+    L.vgx_graph_set_sample_indices.argtypes = [vp, i32, i32, pi32]
+    L.vgx_submap_info.argtypes = [vp, u32, pf, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.vgx_submap_draw_samples.argtypes = [vp, u32, i32, i32, pi32]
     L.vgx_graph_num_registration_residuals.argtypes = [vp, C.POINTER(C.c_int64),
                                                        C.POINTER(C.c_int64)]
     L.vgx_graph_eval.argtypes = [vp, i32, pd, pd, pd]

@@ -112,8 +112,23 @@ class Context:
         self._check(self._L.vgx_submap_block_count(self._h, int(submap_id), C.byref(n)))
         return n.value
 
-    def submap_download(self, submap_id, vps=16):
-        n = self.submap_block_count(submap_id)
+    def submap_info(self, submap_id):
+        """(voxel_size, voxels_per_side, n_blocks, finished)"""
+        vs = C.c_float(0); vps = C.c_int(0); n = C.c_int(0); fin = C.c_int(0)
+        self._check(self._L.vgx_submap_info(self._h, int(submap_id), C.byref(vs), C.byref(vps),
+                                            C.byref(n), C.byref(fin)))
+        return vs.value, vps.value, n.value, bool(fin.value)
+
+    def submap_draw_samples(self, submap_id, point_type, n):
+        """WeightedSampler::getRandomItem n times on the submap's generator -> indices."""
+        idx = np.zeros(n, np.int32)
+        self._check(self._L.vgx_submap_draw_samples(self._h, int(submap_id), int(point_type), int(n),
+                                                    _p(idx, C.c_int32)))
+        return idx
+
+    def submap_download(self, submap_id, vps=None):
+        _, vps_dev, n, _ = self.submap_info(submap_id)
+        vps = vps_dev   # buffers are sized from the layer's own voxels_per_side
         idx = np.zeros((n, 3), np.int32)
         d = np.zeros((n, vps ** 3), np.float32); w = np.zeros((n, vps ** 3), np.float32)
         got = C.c_int(0)
@@ -207,6 +222,23 @@ class Context:
         cfg = cfg or self.reg_config()
         self._check(self._L.vgx_graph_set_registration_constraints(self._h, len(a), _p(a, C.c_uint32),
                                                                    _p(b, C.c_uint32), C.byref(cfg)))
+
+    def graph_set_registration_constraints_v(self, ref_ids, read_ids, cfgs):
+        a = np.ascontiguousarray(ref_ids, np.uint32); b = np.ascontiguousarray(read_ids, np.uint32)
+        arr = (RegConfig * len(a))(*cfgs)
+        self._check(self._L.vgx_graph_set_registration_constraints_v(self._h, len(a), _p(a, C.c_uint32),
+                                                                     _p(b, C.c_uint32), arr))
+
+    def graph_get_sample_indices(self, constraint, max_n):
+        idx = np.zeros(max(max_n, 1), np.int32); n = C.c_int(0)
+        self._check(self._L.vgx_graph_get_sample_indices(self._h, int(constraint), int(max_n),
+                                                         _p(idx, C.c_int32), C.byref(n)))
+        return idx[:n.value].copy()
+
+    def graph_set_sample_indices(self, constraint, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        self._check(self._L.vgx_graph_set_sample_indices(self._h, int(constraint), len(idx),
+                                                         _p(idx, C.c_int32)))
 
     def graph_num_registration_residuals(self):
         a = C.c_int64(0); b = C.c_int64(0)
@@ -382,7 +414,7 @@ class PoseGraph:
         self._frames = set()
         self._relative = []
         self._registration = []   # (ref_id, read_id) residual blocks, mirrored ones included
-        self._reg_cfg = None
+        self._reg_cfgs = []       # one RegistrationCostFunction::Config per residual block
         self._dirty = True
         self.solver_summaries = []
         self.solver_options = ctx.solver_options()   # pose_graph.cpp:91-97 defaults
@@ -440,14 +472,14 @@ class PoseGraph:
         cfg = self.ctx.reg_config(registration_point_type=int(config.registration_point_type),
                                   no_correspondence_cost=float(config.no_correspondence_cost),
                                   sampling_ratio=float(config.sampling_ratio))
-        self._reg_cfg = cfg
-        self._registration.append((a, b))
+        self._registration.append((a, b)); self._reg_cfgs.append(cfg)
         if config.registration_point_type == K_ISOSURFACE_POINTS:   # pose_graph.cpp:63-71
-            self._registration.append((b, a))
+            self._registration.append((b, a)); self._reg_cfgs.append(cfg)
         self._dirty = True
 
     def resetRegistrationConstraints(self):
         self._registration = []
+        self._reg_cfgs = []
         self._dirty = True
 
     def _sync(self):
@@ -462,9 +494,9 @@ class PoseGraph:
                                                   np.array([r[2] for r in self._relative]),
                                                   np.array([r[3] for r in self._relative]))
             if self._registration:
-                self.ctx.graph_set_registration_constraints([r[0] for r in self._registration],
-                                                            [r[1] for r in self._registration],
-                                                            self._reg_cfg)
+                self.ctx.graph_set_registration_constraints_v([r[0] for r in self._registration],
+                                                              [r[1] for r in self._registration],
+                                                              self._reg_cfgs)
             self._dirty = False
         return ids
 

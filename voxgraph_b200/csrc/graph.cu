@@ -48,7 +48,9 @@ struct VgxGraph {
   std::map<uint32_t, int> index;
   std::vector<VgxRelEdge> rel;
   std::vector<uint32_t> reg_ref, reg_read;
-  vgx_reg_config reg_cfg;
+  std::vector<vgx_reg_config> reg_cfgs;              // one per residual block
+  std::vector<std::vector<int32_t>> samples;         // sampling mode: indices in use per block
+  std::vector<std::vector<int32_t>> sample_override; // vgx_graph_set_sample_indices
   bool dirty = true;
 
   // derived
@@ -85,6 +87,8 @@ struct VgxGraph {
   double* d_step = nullptr;
   LmState* d_state = nullptr;
   LmState* h_state = nullptr;
+  float* d_sample_pts = nullptr;   // gathered unit-major points of the local sampled blocks
+  int32_t* d_sample_idx = nullptr;
 };
 
 static void free_tables(VgxGraph* g) {
@@ -95,6 +99,8 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_packed[0]); cudaFree(g->d_packed[1]);
   cudaFree(g->d_A); cudaFree(g->d_scale); cudaFree(g->d_diag); cudaFree(g->d_gs); cudaFree(g->d_step);
   cudaFree(g->d_state);
+  cudaFree(g->d_sample_pts); cudaFree(g->d_sample_idx);
+  g->d_sample_pts = nullptr; g->d_sample_idx = nullptr;
   if (g->h_state) cudaFreeHost(g->h_state);
   g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_cta_tile_begin = nullptr;
   g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
@@ -119,7 +125,6 @@ void vgx_graph_invalidate_registration(vgx_ctx* c) {
 static VgxGraph* graph_of(vgx_ctx* c) {
   if (!c->graph) {
     c->graph = new (std::nothrow) VgxGraph();
-    if (c->graph) vgx_reg_config_default(&c->graph->reg_cfg);
   }
   return c->graph;
 }
@@ -994,10 +999,14 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   const int P = (int)g->reg_ref.size();
   // ---- shard registration constraints over ranks: greedy by descending point count
   std::vector<RegConstraintDev> all(P);
+  std::vector<uint8_t> is_sampled(P, 0);
   g->zero_weight = false;
   g->residuals_global = 0;
+  g->samples.assign(P, std::vector<int32_t>());
+  g->sample_override.resize(P);
   for (int i = 0; i < P; ++i) {
-    int rc = vgx_fill_constraint(c, g->reg_ref[i], g->reg_read[i], &g->reg_cfg, &all[i]);
+    bool sampled = false;
+    int rc = vgx_fill_constraint(c, g->reg_ref[i], g->reg_read[i], &g->reg_cfgs[i], &all[i], &sampled);
     if (rc != VGX_OK) return rc;
     auto ia = g->index.find(g->reg_ref[i]);
     auto ib = g->index.find(g->reg_read[i]);
@@ -1007,6 +1016,20 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
     all[i].read_node = ib->second;
     if (all[i].n == 0 || all[i].factor == 0.0) g->zero_weight = true;
     g->residuals_global += all[i].n;
+    if (sampled && all[i].n > 0) {
+      // Sampling mode: one draw per (re)build of the constraint list, on EVERY rank and in list
+      // order, so the per-submap generators advance identically everywhere (see the header).
+      is_sampled[i] = 1;
+      VgxPoints& p = c->find(g->reg_ref[i])->points[g->reg_cfgs[i].registration_point_type];
+      if ((int)g->sample_override[i].size() == all[i].n) {
+        g->samples[i] = g->sample_override[i];
+        for (int32_t v : g->samples[i])
+          if (v < 0 || v >= p.n) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_graph_set_sample_indices: index out of range");
+      } else {
+        g->samples[i].resize(all[i].n);
+        vgx_points_draw(p, all[i].n, g->samples[i].data());
+      }
+    }
   }
   std::vector<int32_t> owner(P, 0), counts(P, 0);
   for (int i = 0; i < P; ++i) counts[i] = all[i].n;
@@ -1023,40 +1046,68 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
     g->residuals_local += all[i].n;
   }
   g->n_local = (int)cons.size();
-  // Cut the local residual index space evenly over the resident CTAs; a tile is the part of one
-  // CTA's share that lies inside one residual block (so tiles never straddle constraints).
-  const int n_ctas_max = vgx_reg_resident_ctas(c->device);
-  const int64_t R = g->residuals_local;
-  int64_t chunk = (R + n_ctas_max - 1) / std::max(n_ctas_max, 1);
-  chunk = std::max<int64_t>(((chunk + VGX_REG_THREADS - 1) / VGX_REG_THREADS) * VGX_REG_THREADS, VGX_REG_THREADS);
-  g->n_ctas = (int)((R + chunk - 1) / chunk);
+  // gather the drawn points of the local sampled blocks into their own unit-major buffers
+  {
+    size_t units = 0, nidx = 0;
+    for (int k = 0; k < g->n_local; ++k)
+      if (is_sampled[g->local[k]]) { units += ((size_t)cons[k].n + 31) / 32; nidx += (size_t)cons[k].n; }
+    if (units > 0) {
+      VGX_CUDA(c, cudaMalloc((void**)&g->d_sample_pts, units * VGX_PT_UNIT_FLOATS * sizeof(float)));
+      VGX_CUDA(c, cudaMalloc((void**)&g->d_sample_idx, nidx * sizeof(int32_t)));
+      size_t uo = 0, io = 0;
+      for (int k = 0; k < g->n_local; ++k) {
+        const int i = g->local[k];
+        if (!is_sampled[i]) continue;
+        const VgxPoints& p = c->find(g->reg_ref[i])->points[g->reg_cfgs[i].registration_point_type];
+        VGX_CUDA(c, cudaMemcpyAsync(g->d_sample_idx + io, g->samples[i].data(), sizeof(int32_t) * cons[k].n,
+                                    cudaMemcpyHostToDevice, c->stream));
+        float* dst = g->d_sample_pts + uo * VGX_PT_UNIT_FLOATS;
+        vgx_launch_reg_gather_samples(c->stream, p.data, g->d_sample_idx + io, cons[k].n, dst);
+        c->launches++;
+        cons[k].pts = dst;
+        uo += ((size_t)cons[k].n + 31) / 32;
+        io += (size_t)cons[k].n;
+      }
+      VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // g->samples[] are pageable host vectors
+    }
+  }
+  // Cut the local residual index space into 32-point units and deal them evenly to the resident
+  // CTAs; a tile is the part of one CTA's run of units that lies inside one residual block (tiles
+  // never straddle constraints and start on a unit boundary = 128-byte aligned SoA slices for TMA).
+  g->grid_capacity = 0;
+  for (const auto& cc : cons)
+    if (cc.grid) g->grid_capacity = std::max(g->grid_capacity, cc.gd0 * cc.gd1 * cc.gd2);
+  const int n_ctas_max = std::max(vgx_reg_resident_ctas(c->device, g->grid_capacity), 1);
+  int64_t U = 0;  // total units
+  for (const auto& cc : cons) U += (cc.n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
+  g->n_ctas = (int)std::min<int64_t>(n_ctas_max, U);
   std::vector<int> cta_tile_begin;
   {
-    int64_t pos = 0;  // global residual index of the current constraint's first point
-    int next_cta = 0;
+    int64_t ubase = 0;  // unit index of the current constraint's first unit
+    int cta = 0;
+    auto cta_end = [&](int k) { return (int64_t)(((__int128)U * (k + 1)) / std::max(g->n_ctas, 1)); };
+    if (g->n_ctas > 0) cta_tile_begin.push_back(0);
     for (int k = 0; k < g->n_local; ++k) {
       tile_begin.push_back((int)tiles.size());
-      int s = 0;
-      while (s < cons[k].n) {
-        const int64_t gpos = pos + s;
-        const int cta = (int)(gpos / chunk);
-        const int64_t cta_end = (int64_t)(cta + 1) * chunk;
-        const int cnt = (int)std::min<int64_t>(cons[k].n - s, cta_end - gpos);
-        while (next_cta <= cta) { cta_tile_begin.push_back((int)tiles.size()); ++next_cta; }
+      const int64_t uc = (cons[k].n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
+      int64_t u = 0;
+      while (u < uc) {
+        while (cta + 1 < g->n_ctas && ubase + u >= cta_end(cta)) { cta_tile_begin.push_back((int)tiles.size()); ++cta; }
+        const int64_t take = std::min<int64_t>(uc - u, cta_end(cta) - (ubase + u));
         RegTile t;
-        t.constraint = k; t.start = s; t.count = cnt; t.pad = 0;
+        t.constraint = k;
+        t.start = (int)(u * VGX_REG_UNIT);
+        t.count = (int)std::min<int64_t>(take * VGX_REG_UNIT, (int64_t)cons[k].n - t.start);
+        t.pad = 0;
         tiles.push_back(t);
-        s += cnt;
+        u += take;
       }
-      pos += cons[k].n;
+      ubase += uc;
     }
     while ((int)cta_tile_begin.size() <= g->n_ctas) cta_tile_begin.push_back((int)tiles.size());
   }
   tile_begin.push_back((int)tiles.size());
   g->n_tiles = (int)tiles.size();
-  g->grid_capacity = 0;
-  for (const auto& cc : cons)
-    if (cc.grid) g->grid_capacity = std::max(g->grid_capacity, cc.gd0 * cc.gd1 * cc.gd2);
   g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
 
   // ---- off-diagonal block index over ALL edges (identical on every rank)
@@ -1123,6 +1174,8 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
   dmalloc((void**)&g->d_counters, sizeof(int) * (size_t)g->n_local);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counters, 0, std::max<size_t>(sizeof(int) * (size_t)g->n_local, 4), st);
+  // a constraint without points owns no tile: its sums must read as zero
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_csum, 0, std::max<size_t>(sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local, 8), st);
   dmalloc((void**)&g->d_xc, sizeof(double) * 4 * N);
   dmalloc((void**)&g->d_packed[0], sizeof(double) * g->packed_len);
   dmalloc((void**)&g->d_packed[1], sizeof(double) * g->packed_len);
@@ -1241,6 +1294,8 @@ extern "C" int vgx_graph_set_nodes(vgx_ctx* c, int n, const uint32_t* ids, const
   g->rel.clear();
   g->reg_ref.clear();
   g->reg_read.clear();
+  g->reg_cfgs.clear();
+  g->sample_override.clear();
   g->dirty = true;
   return VGX_OK;
 }
@@ -1295,20 +1350,50 @@ extern "C" int vgx_graph_set_relative_edges(vgx_ctx* c, int m, const uint32_t* i
   return VGX_OK;
 }
 
-extern "C" int vgx_graph_set_registration_constraints(vgx_ctx* c, int p, const uint32_t* ref_ids,
-                                                      const uint32_t* read_ids,
-                                                      const vgx_reg_config* cfg) {
+static int set_registration(vgx_ctx* c, int p, const uint32_t* ref_ids, const uint32_t* read_ids,
+                            const vgx_reg_config* cfgs, bool per_constraint) {
   if (!c || p < 0 || (p > 0 && (!ref_ids || !read_ids))) return VGX_ERR_INVALID;
+  if (per_constraint && p > 0 && !cfgs) return VGX_ERR_INVALID;
   VgxGraph* g = graph_of(c);
   if (!g) return VGX_ERR_NOMEM;
-  if (cfg) g->reg_cfg = *cfg;
   for (int i = 0; i < p; ++i) {
     if (ref_ids[i] == read_ids[i]) VGX_FAIL(c, VGX_ERR_INVALID, "cannot constrain a submap to itself");
     if (!g->index.count(ref_ids[i]) || !g->index.count(read_ids[i]))
       VGX_FAIL(c, VGX_ERR_NOT_FOUND, "graph contains no node for a registration constraint's submap");
   }
+  vgx_reg_config dflt;
+  vgx_reg_config_default(&dflt);
   g->reg_ref.assign(ref_ids, ref_ids + p);
   g->reg_read.assign(read_ids, read_ids + p);
+  g->reg_cfgs.resize(p);
+  for (int i = 0; i < p; ++i) g->reg_cfgs[i] = per_constraint ? cfgs[i] : (cfgs ? cfgs[0] : dflt);
+  g->sample_override.assign(p, std::vector<int32_t>());
+  g->dirty = true;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_set_registration_constraints(vgx_ctx* c, int p, const uint32_t* ref_ids,
+                                                      const uint32_t* read_ids,
+                                                      const vgx_reg_config* cfg) {
+  return set_registration(c, p, ref_ids, read_ids, cfg, false);
+}
+
+extern "C" int vgx_graph_set_registration_constraints_v(vgx_ctx* c, int p, const uint32_t* ref_ids,
+                                                        const uint32_t* read_ids,
+                                                        const vgx_reg_config* cfgs) {
+  return set_registration(c, p, ref_ids, read_ids, cfgs, true);
+}
+
+extern "C" int vgx_graph_set_sample_indices(vgx_ctx* c, int constraint, int n, const int32_t* indices) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxGraph* g = graph_of(c);
+  if (!g) return VGX_ERR_NOMEM;
+  if (constraint < 0 || constraint >= (int)g->reg_ref.size() || n < 0 || (n > 0 && !indices))
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_graph_set_sample_indices: invalid argument");
+  if (g->reg_cfgs[constraint].sampling_ratio == -1.0f)
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_graph_set_sample_indices: the constraint is not in sampling mode");
+  g->sample_override.resize(g->reg_ref.size());
+  g->sample_override[constraint].assign(indices, indices + n);
   g->dirty = true;
   return VGX_OK;
 }
@@ -1319,6 +1404,19 @@ extern "C" int vgx_graph_num_registration_residuals(vgx_ctx* c, int64_t* local, 
   if (rc != VGX_OK) return rc;
   if (local) *local = g->residuals_local;
   if (global) *global = g->residuals_global;
+  return VGX_OK;
+}
+
+extern "C" int vgx_graph_get_sample_indices(vgx_ctx* c, int constraint, int max_n, int32_t* indices, int* n) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  if (constraint < 0 || constraint >= (int)g->samples.size())
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_graph_get_sample_indices: invalid constraint index");
+  const std::vector<int32_t>& v = g->samples[constraint];
+  if (n) *n = (int)v.size();
+  if ((int)v.size() > max_n) VGX_FAIL(c, VGX_ERR_CAPACITY, "vgx_graph_get_sample_indices: max_n too small");
+  if (indices && !v.empty()) memcpy(indices, v.data(), sizeof(int32_t) * v.size());
   return VGX_OK;
 }
 

@@ -3,6 +3,8 @@
 #include "registration.cuh"
 #include "registration_kernels.h"
 
+#include <stdlib.h>
+
 // ------------------------------------------------------------------ emit mode
 // One thread per registration point; writes the normalised residual and the two 1x4
 // Jacobian rows exactly as Evaluate leaves them for Ceres (cpp:254-291).
@@ -11,8 +13,9 @@ reg_emit_kernel(RegConstraintDev C, RegPoseConst P, double* __restrict__ residua
                 double* __restrict__ jac_ref, double* __restrict__ jac_read) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C.n) return;
-  const float xi = __ldg(C.px + i), yi = __ldg(C.py + i), zi = __ldg(C.pz + i);
-  const float dist = __ldg(C.pd + i), w = __ldg(C.pw + i);
+  const float* pp = C.pts + vgx_pt_index((size_t)i, 0);
+  const float xi = __ldg(pp), yi = __ldg(pp + 32), zi = __ldg(pp + 64);
+  const float dist = __ldg(pp + 96), w = __ldg(pp + 128);
   RegPointResult R;
   if (jac_ref || jac_read) R = vgx_reg_point<true>(C, P, xi, yi, zi, dist, w);
   else R = vgx_reg_point<false>(C, P, xi, yi, zi, dist, w);
@@ -49,10 +52,46 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 
 #define VGX_STAGE_STRIDE 36  // doubles per component row (32 points + pad: 2-way = optimal for 8 B)
 
-// Persistent CTAs: the residual index space is cut evenly over the grid (148 x resident CTAs per
-// SM); a CTA walks its tiles (a tile never straddles two residual blocks).  Per tile: the
-// reading submap's dense block grid is staged in shared memory, points stream through
-// transform -> voxel index -> grid lookup -> one octet -> residual/Jacobian -> Gram MMA.
+// ---- TMA (1-D bulk copy) + mbarrier primitives, sm_100a PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "VGX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra VGX_DONE;\n"
+      "bra VGX_WAIT;\n"
+      "VGX_DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (SASS UBLKCP); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Registration reduce kernel, v4.  Persistent CTAs; the local residual index space is cut into
+// 32-point units that are dealt evenly to the CTAs (a tile = a CTA's run of units inside one
+// residual block).  Inside a tile every warp runs its own software pipeline over the units
+// u = warp, warp + W, ...:
+//   * the unit's points (640 contiguous bytes of the unit-major AoSoA layout) are brought into a
+//     per-warp 4-slot shared-memory ring by ONE cp.async.bulk (TMA 1-D) completing on an
+//     mbarrier, three units ahead - the point loads never touch the LSU path of the math warps;
+//   * stage A(u+1): transform -> voxel index -> block-grid lookup (shared memory) -> the octet's
+//     two LDG.128 are ISSUED;  stage B(u): the octet issued one iteration earlier is consumed:
+//     B1 coefficients, residual, Jacobian, Gram staging + 8 DMMA.  The gather latency of unit
+//     u+1 is hidden behind the arithmetic of unit u inside the same warp.
+// The last unit is zero-padded to 32 points (weight 0 -> zero contribution), so the
+// loop carries no "active" predicate.  Warps never synchronise with each other inside a tile.
 template <bool kJacobian>
 __global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
@@ -61,99 +100,144 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   int* __restrict__ counters, double* __restrict__ partials,
                   double* __restrict__ csum, int grid_capacity) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
+  constexpr int kRing = VGX_REG_RING;
+  __shared__ __align__(128) float s_ring[kWarps][kRing][5][32];
+  __shared__ __align__(8) unsigned long long s_bar[kWarps][kRing];
   __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
   __shared__ double s_gram[kWarps][64];
+  __shared__ RegConstraintDev s_C;
+  __shared__ RegPoseConst s_P;
   __shared__ int s_last;
   extern __shared__ int32_t s_grid[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kRing; ++k) mbar_init(smem_u32(&s_bar[warp][k]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t ring0 = smem_u32(&s_ring[warp][0][0][0]);
+  const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
+  const float* ringf = &s_ring[warp][0][0][0];
+  double* stage_w = &s_stage[warp][0][lane];
+  const double* stage_r = &s_stage[warp][grp < 6 ? grp : 0][tig];
+  uint32_t it = 0;   // units consumed by this warp so far: ring slot = it % kRing, parity = (it / kRing) & 1
   int grid_of = -1;  // constraint whose block grid is currently staged
 
   for (int tile = cta_tile_begin[blockIdx.x]; tile < cta_tile_begin[blockIdx.x + 1]; ++tile) {
     const RegTile T = tiles[tile];
-    const RegConstraintDev C = constraints[T.constraint];
-    const RegPoseConst P = poses[T.constraint];
-    const int cells = C.gd0 * C.gd1 * C.gd2;
-    const bool use_grid = C.grid != nullptr && cells <= grid_capacity;
+    __syncthreads();  // previous tile: every warp is out of its loop (s_C / s_P / s_grid readers)
+    {
+      constexpr int kWc = (int)(sizeof(RegConstraintDev) / 4), kWp = (int)(sizeof(RegPoseConst) / 4);
+      for (int k = threadIdx.x; k < kWc + kWp; k += VGX_REG_THREADS) {
+        if (k < kWc)
+          reinterpret_cast<uint32_t*>(&s_C)[k] =
+              __ldg(reinterpret_cast<const uint32_t*>(constraints + T.constraint) + k);
+        else
+          reinterpret_cast<uint32_t*>(&s_P)[k - kWc] =
+              __ldg(reinterpret_cast<const uint32_t*>(poses + T.constraint) + (k - kWc));
+      }
+    }
+    __syncthreads();
+    const int cells = s_C.gd0 * s_C.gd1 * s_C.gd2;
+    const bool use_grid = s_C.grid != nullptr && cells <= grid_capacity;
     if (use_grid && grid_of != T.constraint) {
-      __syncthreads();  // previous tile's readers are done
-      for (int k = threadIdx.x; k < cells; k += VGX_REG_THREADS) s_grid[k] = __ldg(C.grid + k);
+      const int32_t* gsrc = s_C.grid;
+      for (int k = threadIdx.x; k < cells; k += VGX_REG_THREADS) s_grid[k] = __ldg(gsrc + k);
       grid_of = T.constraint;
       __syncthreads();
     }
+    const RegPoseConst P = s_P;
     double d0 = 0.0, d1 = 0.0;
-    const int end = T.start + T.count;
-    const size_t vox_shift = 3 * C.vps_shift;
-#if VGX_REG_PREFETCH
-    // software pipeline: the next round's point is loaded while this round is computed
-    float nx, ny, nz, nd, nw;
-    {
-      const int i0 = T.start + threadIdx.x;
-      const int ic0 = i0 < end ? i0 : T.start;
-      nx = __ldg(C.px + ic0); ny = __ldg(C.py + ic0); nz = __ldg(C.pz + ic0);
-      nd = __ldg(C.pd + ic0); nw = __ldg(C.pw + ic0);
-    }
-#endif
-    for (int base = T.start; base < end; base += VGX_REG_THREADS) {
-      const int i = base + threadIdx.x;
-      const bool act = i < end;
-#if VGX_REG_PREFETCH
-      const float xi = nx, yi = ny, zi = nz, dist = nd, w = nw;
-      {
-        const int in = i + VGX_REG_THREADS;
-        const int icn = in < end ? in : T.start;
-        nx = __ldg(C.px + icn); ny = __ldg(C.py + icn); nz = __ldg(C.pz + icn);
-        nd = __ldg(C.pd + icn); nw = __ldg(C.pw + icn);
+    const int n_units = (T.count + 31) >> 5;
+    const int my_units = warp < n_units ? (n_units - warp + kWarps - 1) / kWarps : 0;
+    const size_t vox_shift = 3 * s_C.vps_shift;
+    const float4* view = reinterpret_cast<const float4*>(s_C.view);
+
+    // producer (lane 0): bring unit j of this warp into ring slot (it + j - j_consumed)
+    auto issue = [&](int j, uint32_t seq) {
+      if (lane == 0) {
+        const uint32_t slot = seq % kRing;
+        const uint32_t bar = bar0 + 8u * slot, dst = ring0 + 640u * slot;
+        const size_t unit = (size_t)(T.start >> 5) + (size_t)(warp + j * kWarps);
+        mbar_expect_tx(bar, 640u);
+        tma_load_1d(dst, s_C.pts + unit * VGX_PT_UNIT_FLOATS, 640u, bar);
       }
-#else
-      const int ic = act ? i : T.start;
-      const float xi = __ldg(C.px + ic), yi = __ldg(C.py + ic), zi = __ldg(C.pz + ic);
-      const float dist = __ldg(C.pd + ic), w = __ldg(C.pw + ic);
-#endif
+    };
+    // stage A: everything up to the ISSUE of the octet loads
+    float4 lo, hi;
+    float ox, oy, oz;
+    bool found;
+    auto stage_a = [&](uint32_t seq, float4& alo, float4& ahi, float& aox, float& aoy, float& aoz,
+                       bool& afound) {
+      const uint32_t slot = seq % kRing;
+      mbar_wait(bar0 + 8u * slot, (seq / kRing) & 1u);
+      const float* sp = ringf + 160 * slot + lane;
       float p0, p1, p2;
-      vgx_reg_transform(P, xi, yi, zi, p0, p1, p2);
+      vgx_reg_transform(P, sp[0], sp[32], sp[64], p0, p1, p2);
       RegLocate L;
-      int slot;
+      int slot_b;
       if (use_grid) {
-        vgx_locate<true>(C, p0, p1, p2, L, s_grid);
-        slot = L.slot;
+        vgx_locate<true>(s_C, p0, p1, p2, L, s_grid);
+        slot_b = L.slot;
       } else {
-        vgx_locate<false>(C, p0, p1, p2, L);
-        slot = vgx_resolve(C, L);
+        vgx_locate<false>(s_C, p0, p1, p2, L);
+        slot_b = vgx_resolve(s_C, L);
       }
-      const bool found = slot >= 0;
-      const size_t lin = ((size_t)(found ? slot : 0) << vox_shift) + L.lin;
-      const float4* o = reinterpret_cast<const float4*>(C.view) + 2 * lin;
+      afound = slot_b >= 0;
+      aox = L.ox; aoy = L.oy; aoz = L.oz;
+      const float qnan = __int_as_float(0x7fc00000);
+      alo = make_float4(qnan, qnan, qnan, qnan);
+      ahi = alo;
+      if (afound) {
+        const float4* o = view + 2 * (((size_t)slot_b << vox_shift) + (size_t)L.lin);
 #if VGX_REG_STREAM_OCTETS
-      // an octet is touched once per evaluation: keep it out of L1 (evict-first)
-      const float4 lo = __ldcs(o), hi = __ldcs(o + 1);
+        alo = __ldcs(o); ahi = __ldcs(o + 1);
 #else
-      const float4 lo = __ldg(o), hi = __ldg(o + 1);
+        alo = __ldg(o); ahi = __ldg(o + 1);
 #endif
+      }
+    };
+
+    if (my_units > 0) {
+#pragma unroll
+      for (int j = 0; j < kRing - 1; ++j)
+        if (j < my_units) issue(j, it + j);
+      stage_a(it, lo, hi, ox, oy, oz, found);
+    }
+    for (int j = 0; j < my_units; ++j, ++it) {
+      // slot of unit j-1 is free: every lane finished its stage B (the __syncwarp after the DMMAs)
+      if (j + kRing - 1 < my_units) issue(j + kRing - 1, it + kRing - 1);
+      float4 nlo, nhi;
+      float nox = 0.f, noy = 0.f, noz = 0.f;
+      bool nfound = false;
+      if (j + 1 < my_units) stage_a(it + 1, nlo, nhi, nox, noy, noz, nfound);
+      // ---- stage B: consume the octet issued one iteration ago
+      const float* sp = ringf + 160 * (it % kRing) + lane;
+      const float xi = sp[0], yi = sp[32], dist = sp[96], w = sp[128];
       const float d[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       const bool ok = found && vgx_octet_ok(d);
-      const RegPointResult R = vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, L.ox, L.oy, L.oz);
-      double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
-      if (act) {
-        v5 = R.r;
-        if (kJacobian) {
-          v0 = (double)R.jr[0]; v1 = (double)R.jr[1]; v2 = (double)R.jr[2];
-          v3 = (double)R.jr[3]; v4 = (double)R.je3;
-        }
-      }
+      const RegPointResult R = vgx_reg_math<kJacobian>(s_C, P, xi, yi, dist, w, ok, d, ox, oy, oz);
       if (kJacobian) {
-        s_stage[warp][0][lane] = v0; s_stage[warp][1][lane] = v1; s_stage[warp][2][lane] = v2;
-        s_stage[warp][3][lane] = v3; s_stage[warp][4][lane] = v4; s_stage[warp][5][lane] = v5;
+        stage_w[0 * VGX_STAGE_STRIDE] = (double)R.jr[0];
+        stage_w[1 * VGX_STAGE_STRIDE] = (double)R.jr[1];
+        stage_w[2 * VGX_STAGE_STRIDE] = (double)R.jr[2];
+        stage_w[3 * VGX_STAGE_STRIDE] = (double)R.jr[3];
+        stage_w[4 * VGX_STAGE_STRIDE] = (double)R.je3;
+        stage_w[5 * VGX_STAGE_STRIDE] = R.r;
         __syncwarp();
 #pragma unroll
         for (int t4 = 0; t4 < 8; ++t4) {
-          const double a = (grp < 6) ? s_stage[warp][grp][4 * t4 + tig] : 0.0;
+          const double a = (grp < 6) ? stage_r[4 * t4] : 0.0;
           dmma_8x8x4(d0, d1, a, a);
         }
         __syncwarp();
       } else {
-        d0 = fma(v5, v5, d0);
+        d0 = fma(R.r, R.r, d0);
+        __syncwarp();
       }
+      lo = nlo; hi = nhi; ox = nox; oy = noy; oz = noz; found = nfound;
     }
     // ---- tile epilogue: warp Gram fragments -> 21 sums -> partials[tile]
     if (kJacobian) {
@@ -165,6 +249,7 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       if (lane == 0) s_gram[warp][0] = d0;
     }
     __syncthreads();
+    const double factor = s_C.factor;
     if (threadIdx.x < VGX_REG_NSUM) {
       // entry e of the 21 sums -> (row, col) of the Gram matrix
       int row = 5, col = 5;
@@ -192,8 +277,7 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
     if (t1 - t0 == 1) {
       if (threadIdx.x < VGX_REG_NSUM)  // single tile: no ticket needed (same thread wrote the partial)
         csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] =
-            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (C.factor * C.factor);
-      __syncthreads();
+            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (factor * factor);
     } else {
       __threadfence();
       __syncthreads();
@@ -207,7 +291,7 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
         if (threadIdx.x < VGX_REG_NSUM) {
           double s = 0;
           for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
-          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (C.factor * C.factor);
+          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (factor * factor);
         }
         if (threadIdx.x == 0) counters[T.constraint] = 0;
       }
@@ -248,21 +332,52 @@ void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const 
                                                                    grid_capacity);
 }
 
-int vgx_reg_resident_ctas(int device) {
-  int sms = 148;
+int vgx_reg_resident_ctas(int device, int grid_capacity) {
+  int sms = 148, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  return sms * VGX_REG_MIN_BLOCKS;
+  const size_t smem = sizeof(int32_t) * (size_t)grid_capacity;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_reduce_kernel<true>, VGX_REG_THREADS,
+                                                    smem) != cudaSuccess || per_sm <= 0)
+    per_sm = VGX_REG_MIN_BLOCKS;
+  static const char* env = getenv("VGX_REG_CTAS_PER_SM");  // tuning override
+  if (env && atoi(env) > 0) per_sm = atoi(env);
+  return sms * per_sm;
+}
+
+// cpp:45-55: num_residuals = int(sampling_ratio * size()) (float product) or size()
+static int reg_num_residuals(const VgxPoints& p, const vgx_reg_config* cfg) {
+  if (cfg->sampling_ratio != -1.0f) return (int)(cfg->sampling_ratio * (float)(size_t)p.n);
+  return p.n;
+}
+
+__global__ void reg_gather_samples_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                          int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((n + 31) & ~31)) return;
+  float x = 0.f, y = 0.f, z = 0.f, d = 0.f, w = 0.f;
+  if (i < n) {
+    const float* sp = src + vgx_pt_index((size_t)idx[i], 0);
+    x = sp[0]; y = sp[32]; z = sp[64]; d = sp[96];
+    w = 1.0f;  // cpp:121 registration_point.weight = 1
+  }
+  float* dp = dst + vgx_pt_index((size_t)i, 0);
+  dp[0] = x; dp[32] = y; dp[64] = z; dp[96] = d; dp[128] = w;
+}
+
+void vgx_launch_reg_gather_samples(cudaStream_t st, const float* src, const int32_t* d_idx, int n,
+                                   float* dst) {
+  if (n <= 0) return;
+  const int padded = (n + 31) & ~31;
+  reg_gather_samples_kernel<<<(padded + 255) / 256, 256, 0, st>>>(src, d_idx, n, dst);
 }
 
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
-                        RegConstraintDev* out) {
+                        RegConstraintDev* out, bool* sampled) {
   if (!cfg) VGX_FAIL(c, VGX_ERR_INVALID, "null registration config");
-  if (cfg->sampling_ratio != -1.0f)
-    VGX_FAIL(c, VGX_ERR_INVALID,
-             "sampling_ratio != -1 (random re-sampling per Evaluate) is not supported; "
-             "pre-sample the registration points on the host");
   if (cfg->registration_point_type < 0 || cfg->registration_point_type > 1)
     VGX_FAIL(c, VGX_ERR_INVALID, "invalid registration_point_type");
+  if (cfg->sampling_ratio != -1.0f && !(cfg->sampling_ratio >= 0.0f))
+    VGX_FAIL(c, VGX_ERR_INVALID, "sampling_ratio must be -1 (all points) or >= 0");
   if (ref_id == read_id) VGX_FAIL(c, VGX_ERR_INVALID, "cannot constrain a submap to itself");
   VgxSubmap* ref = c->find(ref_id);
   VgxSubmap* rd = c->find(read_id);
@@ -270,9 +385,10 @@ int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx
   if (!rd->finished || !rd->d_view)
     VGX_FAIL(c, VGX_ERR_INVALID, "registration constraint: reading submap is not finished");
   const VgxPoints& p = ref->points[cfg->registration_point_type];
+  const bool is_sampled = cfg->sampling_ratio != -1.0f;
   RegConstraintDev C;
-  C.px = p.x; C.py = p.y; C.pz = p.z; C.pd = p.dist; C.pw = p.w;
-  C.n = p.n;
+  C.pts = is_sampled ? nullptr : p.data;
+  C.n = reg_num_residuals(p, cfg);
   C.ref_node = -1; C.read_node = -1;
   C.hash = rd->hash;
   C.view = rd->d_view;
@@ -284,9 +400,12 @@ int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx
   C.gd0 = rd->grid_dim[0]; C.gd1 = rd->grid_dim[1]; C.gd2 = rd->grid_dim[2];
   C.vps_shift = 0;
   while ((1 << C.vps_shift) < rd->vps) C.vps_shift++;
-  C.factor = (p.sum_w != 0.0) ? (double)p.n / p.sum_w : 0.0;
+  // cpp:274 factor = num_residuals / summed_reference_weight; sampled points all weigh 1
+  if (is_sampled) C.factor = (C.n > 0 && p.n > 0) ? 1.0 : 0.0;
+  else C.factor = (p.sum_w != 0.0) ? (double)p.n / p.sum_w : 0.0;
   C.no_corr = cfg->no_correspondence_cost;
   *out = C;
+  if (sampled) *sampled = is_sampled;
   return VGX_OK;
 }
 
@@ -303,7 +422,8 @@ extern "C" int vgx_reg_num_residuals(vgx_ctx* c, uint32_t ref_id, const vgx_reg_
   VgxSubmap* ref = c->find(ref_id);
   if (!ref) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_reg_num_residuals: unknown submap");
   if (cfg->registration_point_type < 0 || cfg->registration_point_type > 1) return VGX_ERR_INVALID;
-  *n = ref->points[cfg->registration_point_type].n;
+  if (cfg->sampling_ratio != -1.0f && !(cfg->sampling_ratio >= 0.0f)) return VGX_ERR_INVALID;
+  *n = reg_num_residuals(ref->points[cfg->registration_point_type], cfg);
   return VGX_OK;
 }
 
@@ -314,16 +434,33 @@ extern "C" int vgx_reg_eval_emit(vgx_ctx* c, uint32_t ref_id, uint32_t read_id,
   if (!c || !ref_pose || !read_pose || !residuals) return VGX_ERR_INVALID;
   VGX_CUDA(c, cudaSetDevice(c->device));
   RegConstraintDev C;
-  int rc = vgx_fill_constraint(c, ref_id, read_id, cfg, &C);
+  bool sampled = false;
+  int rc = vgx_fill_constraint(c, ref_id, read_id, cfg, &C, &sampled);
   if (rc != VGX_OK) return rc;
   if (C.n == 0) return VGX_ZERO_WEIGHT;  // summed weight 0 -> Evaluate returns false
   if (C.factor == 0.0) return VGX_ZERO_WEIGHT;
-  RegPoseConst P;
-  vgx_reg_pose_setup<TrigHostLibm>(ref_pose, read_pose, P);
   const size_t K = (size_t)C.n;
   const size_t Kp = (K + 3) & ~(size_t)3;  // keep the Jacobian blocks 32-byte aligned
-  rc = c->ensure_scratch(9 * Kp * sizeof(double));
+  const size_t units = (K + 31) / 32;
+  const size_t sample_bytes = sampled ? ((units * VGX_PT_UNIT_FLOATS * sizeof(float) + Kp * sizeof(int32_t) + 255) & ~(size_t)255) : 0;
+  rc = c->ensure_scratch(9 * Kp * sizeof(double) + sample_bytes);
   if (rc != VGX_OK) return rc;
+  if (sampled) {
+    // cpp:118-122: every Evaluate draws its points anew from the reference submap's sampler
+    VgxPoints& p = c->find(ref_id)->points[cfg->registration_point_type];
+    rc = c->ensure_pinned(Kp * sizeof(int32_t));
+    if (rc != VGX_OK) return rc;
+    VGX_CUDA(c, cudaStreamSynchronize(c->stream));
+    vgx_points_draw(p, (int)K, (int32_t*)c->h_pinned);
+    float* d_pts = (float*)((char*)c->d_scratch + 9 * Kp * sizeof(double));
+    int32_t* d_idx = (int32_t*)(d_pts + units * VGX_PT_UNIT_FLOATS);
+    VGX_CUDA(c, cudaMemcpyAsync(d_idx, c->h_pinned, K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    vgx_launch_reg_gather_samples(c->stream, p.data, d_idx, (int)K, d_pts);
+    c->launches++;
+    C.pts = d_pts;
+  }
+  RegPoseConst P;
+  vgx_reg_pose_setup<TrigHostLibm>(ref_pose, read_pose, P);
   double* d_r = (double*)c->d_scratch;
   double* d_jr = jac_ref ? d_r + Kp : nullptr;
   double* d_je = jac_read ? d_r + 5 * Kp : nullptr;

@@ -24,7 +24,7 @@ struct RegPoseConst {
 
 // Reading-submap view + reference points of one residual block.
 struct RegConstraintDev {
-  const float *px, *py, *pz, *pd, *pw;  // reference registration points (SoA)
+  const float* pts;    // reference registration points, unit-major AoSoA (vgx_internal.h VgxPoints)
   int n;
   int ref_node, read_node;
   VgxHash hash;        // reading submap block hash

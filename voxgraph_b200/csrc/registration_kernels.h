@@ -6,13 +6,16 @@
 struct RegConstraintDev;
 struct RegPoseConst;
 
-#define VGX_REG_THREADS 256
+#ifndef VGX_REG_THREADS
+#define VGX_REG_THREADS 128        // 4 warps per CTA, each with its own TMA ring + software pipeline
+#endif
 #ifndef VGX_REG_MIN_BLOCKS
-#define VGX_REG_MIN_BLOCKS 3       // resident CTAs per SM the register budget is sized for
+#define VGX_REG_MIN_BLOCKS 5       // resident CTAs per SM the register budget is sized for
 #endif
-#ifndef VGX_REG_PREFETCH
-#define VGX_REG_PREFETCH 0         // software-pipelined point loads
+#ifndef VGX_REG_RING
+#define VGX_REG_RING 4             // point-slice ring slots per warp (units in flight = RING - 1)
 #endif
+#define VGX_REG_UNIT 32            // points per unit = one warp iteration; tiles are cut on unit boundaries
 #ifndef VGX_REG_STREAM_OCTETS
 #define VGX_REG_STREAM_OCTETS 0   // ld.global.cs for the octet fetch
 #endif
@@ -34,6 +37,14 @@ void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const 
                            const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
                            const int* tile_begin, int* counters, double* partials, double* csum,
                            int grid_capacity, bool jacobian);
-int vgx_reg_resident_ctas(int device);
+// persistent grid size: SMs x CTAs that are co-resident with `grid_capacity` cells of dynamic smem
+int vgx_reg_resident_ctas(int device, int grid_capacity);
+// Fills the descriptor of one (reference -> reading) residual block.  Deterministic mode: pts / n /
+// factor describe all registration points.  Sampling mode (*sampled = true): n = int(ratio * K),
+// factor = 1 (all weights forced to 1) and pts is left null for the caller, who draws the
+// indices (vgx_points_draw) and gathers them (vgx_launch_reg_gather_samples).
 int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx_reg_config* cfg,
-                        RegConstraintDev* out);
+                        RegConstraintDev* out, bool* sampled = nullptr);
+// dst (unit-major, ceil(n/32) units) <- the n points of src selected by d_idx, weight forced to 1
+void vgx_launch_reg_gather_samples(cudaStream_t st, const float* src, const int32_t* d_idx, int n,
+                                   float* dst);

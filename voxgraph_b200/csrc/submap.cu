@@ -74,7 +74,7 @@ extern "C" int vgx_ctx_create(int device, vgx_ctx** out) {
 }
 
 static void free_points(VgxPoints& p) {
-  if (p.x) cudaFree(p.x);  // one allocation holds all five arrays
+  if (p.data) cudaFree(p.data);
   p = VgxPoints();
 }
 
@@ -400,6 +400,18 @@ extern "C" int vgx_submap_block_count(vgx_ctx* c, uint32_t id, int* n) {
   return VGX_OK;
 }
 
+extern "C" int vgx_submap_info(vgx_ctx* c, uint32_t id, float* voxel_size, int* vps, int* n_blocks,
+                               int* finished) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_info: unknown submap");
+  if (voxel_size) *voxel_size = s->voxel_size;
+  if (vps) *vps = s->vps;
+  if (n_blocks) *n_blocks = s->n_blocks;
+  if (finished) *finished = s->finished ? 1 : 0;
+  return VGX_OK;
+}
+
 extern "C" int vgx_submap_download(vgx_ctx* c, uint32_t id, int max_blocks, int32_t* block_idx,
                                    float* distance, float* weight, int* n_out) {
   if (!c) return VGX_ERR_INVALID;
@@ -444,25 +456,28 @@ extern "C" int vgx_submap_upload_points(vgx_ctx* c, uint32_t id, int type, int n
   free_points(p);
   vgx_graph_invalidate_registration(c);
   if (n == 0) return VGX_OK;
-  // SoA staging on the host (pinned), one device allocation for the five arrays
-  const size_t stride = ((size_t)n + 31) & ~(size_t)31;
-  int rc = c->ensure_pinned(5 * stride * sizeof(float));
+  // unit-major AoSoA staging on the host (pinned): unit u = {x[32], y[32], z[32], d[32], w[32]}
+  const size_t units = ((size_t)n + VGX_PT_UNIT - 1) / VGX_PT_UNIT;
+  const size_t floats = units * VGX_PT_UNIT_FLOATS;
+  int rc = c->ensure_pinned(floats * sizeof(float));
   if (rc != VGX_OK) return rc;
   float* h = (float*)c->h_pinned;
+  memset(h, 0, floats * sizeof(float));
   double sum_w = 0;
+  std::vector<double> cumulative((size_t)n);
   for (int i = 0; i < n; ++i) {
-    h[i] = xyz[3 * (size_t)i];
-    h[stride + i] = xyz[3 * (size_t)i + 1];
-    h[2 * stride + i] = xyz[3 * (size_t)i + 2];
-    h[3 * stride + i] = distance[i];
-    h[4 * stride + i] = weight[i];
+    float* u = h + vgx_pt_index((size_t)i, 0);
+    u[0] = xyz[3 * (size_t)i];
+    u[32] = xyz[3 * (size_t)i + 1];
+    u[64] = xyz[3 * (size_t)i + 2];
+    u[96] = distance[i];
+    u[128] = weight[i];
     sum_w += (double)weight[i];  // cpp:124, in point order
+    cumulative[i] = sum_w;       // WeightedSampler::addItem (weighted_sampler_inl.h:6-17)
   }
-  for (size_t i = n; i < stride; ++i)
-    for (int k = 0; k < 5; ++k) h[k * stride + i] = 0.f;
   float* d = nullptr;
-  VGX_CUDA(c, cudaMalloc(&d, 5 * stride * sizeof(float)));
-  cudaError_t e = cudaMemcpyAsync(d, h, 5 * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  VGX_CUDA(c, cudaMalloc(&d, floats * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d, h, floats * sizeof(float), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
     cudaFree(d);
@@ -470,7 +485,38 @@ extern "C" int vgx_submap_upload_points(vgx_ctx* c, uint32_t id, int type, int n
     return VGX_ERR_CUDA;
   }
   p.n = n;
-  p.x = d; p.y = d + stride; p.z = d + 2 * stride; p.dist = d + 3 * stride; p.w = d + 4 * stride;
+  p.data = d;
   p.sum_w = sum_w;
+  p.cumulative_w.swap(cumulative);
+  return VGX_OK;
+}
+
+// ------------------------------------------------------------------ WeightedSampler
+// weighted_sampler_inl.h:19-28: r = uniform_real_distribution<double>(0,1)(mt19937),
+// index = upper_bound(cumulative, r * cumulative.back()).  std::mt19937's default seed (5489)
+// and uniform_real_distribution are what the reference instantiates (weighted_sampler.h:34-36).
+// fl(r * back) can round up to back itself, where upper_bound returns end(): the reference then
+// indexes one past the last item; clamped here.
+void vgx_points_draw(VgxPoints& p, int count, int32_t* idx) {
+  std::uniform_real_distribution<double> uniform(0.0, 1.0);
+  const std::vector<double>& cw = p.cumulative_w;
+  for (int i = 0; i < count; ++i) {
+    const double r = uniform(p.rng);
+    const double t = r * cw.back();
+    size_t k = (size_t)(std::upper_bound(cw.begin(), cw.end(), t) - cw.begin());
+    if (k >= cw.size()) k = cw.size() - 1;
+    idx[i] = (int32_t)k;
+  }
+}
+
+extern "C" int vgx_submap_draw_samples(vgx_ctx* c, uint32_t id, int type, int n, int32_t* indices) {
+  if (!c) return VGX_ERR_INVALID;
+  if (type < 0 || type > 1 || n < 0 || (n > 0 && !indices))
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_draw_samples: invalid argument");
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_draw_samples: unknown submap");
+  VgxPoints& p = s->points[type];
+  if (p.n == 0) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_draw_samples: the submap has no registration points");
+  vgx_points_draw(p, n, indices);
   return VGX_OK;
 }

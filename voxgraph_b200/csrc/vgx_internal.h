@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -70,11 +71,22 @@ __device__ __forceinline__ int vgx_hash_find(const VgxHash& h, int bx, int by, i
 #endif
 
 // ------------------------------------------------------------------ submap store
-struct VgxPoints {  // WeightedSampler<RegistrationPoint> as SoA
+// WeightedSampler<RegistrationPoint> in HBM, "unit-major" AoSoA: 32 points per unit,
+// unit u = float[5][32] = {x[32], y[32], z[32], distance[32], weight[32]} = 640 contiguous
+// bytes, so one cp.async.bulk (TMA 1-D) brings a warp's whole unit into shared memory and a warp
+// reading lane-wise is coalesced.  Zero padded to a whole unit (weight 0 = no contribution).
+#define VGX_PT_UNIT 32
+#define VGX_PT_UNIT_FLOATS 160
+struct VgxPoints {
   int n = 0;
-  float *x = nullptr, *y = nullptr, *z = nullptr, *dist = nullptr, *w = nullptr;
-  double sum_w = 0;  // summed_reference_weight (cpp:124), sequential double sum
+  float* data = nullptr;        // ceil(n / 32) units
+  double sum_w = 0;             // summed_reference_weight (cpp:124), sequential double sum
+  std::vector<double> cumulative_w;  // WeightedSampler::cumulative_item_weights_ (host, sampling mode)
+  std::mt19937 rng;                  // WeightedSampler::random_number_generator_ (default seed)
 };
+__host__ __device__ __forceinline__ size_t vgx_pt_index(size_t i, int component) {
+  return (i >> 5) * VGX_PT_UNIT_FLOATS + (size_t)component * VGX_PT_UNIT + (i & 31);
+}
 
 struct VgxSubmap {
   uint32_t id = 0;
@@ -176,6 +188,8 @@ struct VgxLaunchScope {
 };
 
 int vgx_submap_build_grid(vgx_ctx* ctx, VgxSubmap* s);
+// WeightedSampler::getRandomItem x count on the sampler's own generator (host)
+void vgx_points_draw(VgxPoints& p, int count, int32_t* idx);
 void vgx_graph_free(vgx_ctx* ctx);
 void vgx_graph_invalidate_registration(vgx_ctx* ctx);
 

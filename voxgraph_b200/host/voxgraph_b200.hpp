@@ -240,14 +240,18 @@ class PoseGraph {
     if (config.information_matrix != IdentityInformation())  // registration_constraint.h:32-34
       throw std::invalid_argument("Registration constraint information matrices that differ from the identity "
                                   "matrix are not yet supported.");
-    registration_cfg_ = config.registration;
+    // the reference keeps one Config per constraint (registration_constraint.h:15-21)
     registration_.emplace_back(config.first_submap_id, config.second_submap_id);
-    if (config.registration.registration_point_type == VGX_POINTS_ISOSURFACE)  // pose_graph.cpp:63-71
+    registration_cfgs_.push_back(config.registration);
+    if (config.registration.registration_point_type == VGX_POINTS_ISOSURFACE) {  // pose_graph.cpp:63-71
       registration_.emplace_back(config.second_submap_id, config.first_submap_id);
+      registration_cfgs_.push_back(config.registration);
+    }
     dirty_ = true;
   }
   void resetRegistrationConstraints() {
     registration_.clear();
+    registration_cfgs_.clear();
     dirty_ = true;
   }
 
@@ -304,12 +308,15 @@ class PoseGraph {
     ctx_.check(vgx_graph_set_relative_edges(ctx_.get(), (int)a.size(), a.data(), b.data(), t.data(), L.data()));
     std::vector<uint32_t> ra, rb;
     for (const auto& r : registration_) { ra.push_back(r.first); rb.push_back(r.second); }
-    vgx_reg_config rc;
-    vgx_reg_config_default(&rc);
-    rc.registration_point_type = registration_cfg_.registration_point_type;
-    rc.sampling_ratio = registration_cfg_.sampling_ratio;
-    rc.no_correspondence_cost = registration_cfg_.no_correspondence_cost;
-    ctx_.check(vgx_graph_set_registration_constraints(ctx_.get(), (int)ra.size(), ra.data(), rb.data(), &rc));
+    std::vector<vgx_reg_config> rcs(registration_cfgs_.size());
+    for (size_t k = 0; k < rcs.size(); ++k) {
+      vgx_reg_config_default(&rcs[k]);
+      rcs[k].registration_point_type = registration_cfgs_[k].registration_point_type;
+      rcs[k].sampling_ratio = registration_cfgs_[k].sampling_ratio;
+      rcs[k].no_correspondence_cost = registration_cfgs_[k].no_correspondence_cost;
+    }
+    ctx_.check(vgx_graph_set_registration_constraints_v(ctx_.get(), (int)ra.size(), ra.data(), rb.data(),
+                                                        rcs.data()));
     dirty_ = false;
   }
 
@@ -317,7 +324,7 @@ class PoseGraph {
   std::map<SubmapID, SubmapNodeConfig> nodes_;
   std::vector<std::pair<RelativePoseConstraintConfig, std::array<double, 16>>> relative_;
   std::vector<std::pair<SubmapID, SubmapID>> registration_;
-  RegistrationCostFunction::Config registration_cfg_;
+  std::vector<RegistrationCostFunction::Config> registration_cfgs_;
   vgx_solver_options options_;
   std::vector<SolverSummary> solver_summaries_;
   bool dirty_ = true;
