@@ -4,11 +4,18 @@
 A "step" is one full evaluation of the registration hot path over every registration
 constraint of the pose graph: per point transform -> 8-voxel brick gather -> trilinear
 interpolation -> residual -> two 1x4 Jacobians -> in-kernel reduction to the per-constraint
-normal-equation blocks -> assembly of the global J^T J / J^T r (+ one NCCL all-reduce for N > 1).
+normal-equation blocks -> assembly of the global J^T J / J^T r (+ one exchange of the packed
+normal equations over NVLink for N > 1).
 
-Workload (N = 1): BASELINE.json configs[1] — 50 submaps / 200 overlapping pairs (400 mirrored
-residual blocks) / 10k isosurface points per block, 0.20 m voxels.  For N > 1 the per-GPU work
-is fixed (weak scaling): N copies of the 50-submap floor, 200*N pairs, sharded over the ranks.
+Workloads
+  config2  BASELINE.json configs[1]: 50 submaps / 200 overlapping pairs (x2 mirrored residual
+           blocks) / 10k isosurface points per block, 0.20 m voxels.  Headline at N = 1.
+  config4  BASELINE.json configs[3]: 200 submaps / 1500 pairs / 20k points / 0.10 m voxels, every
+           submap shared by all ranks, constraints sharded (STRONG scaling).  Headline at N > 1;
+           at N = 1 it is measured as a second leg and reported inside the kept dicts
+           (`e2e.config4`, `roofline.config4`) so the 1 -> 8 curve has its own N = 1 point.
+At N > 1 rank 0 re-evaluates the full problem on one GPU (vgx_comm_suspend) and the line carries
+`e2e.parity_vs_single_rank`; the run fails when it exceeds 1e-12.
 
   python bench.py --gpus 1 --steps 20 --warmup 3
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -17,6 +24,7 @@ is fixed (weak scaling): N copies of the 50-submap floor, 200*N pairs, sharded o
 import argparse
 import json
 import os
+import pickle
 import subprocess
 import sys
 import threading
@@ -32,6 +40,12 @@ ALGO_BYTES_PER_RESIDUAL = 84  # 20 B point + 8 corners x (4 B 
 ALGO_BYTES_PER_TSDF_UPDATE = 16
 _REAL_STDOUT = sys.stdout
 
+WORKLOADS = {
+    # name: (submaps, pairs, points, voxel size, seed, BASELINE.json configs index)
+    "config2": dict(submaps=50, pairs=200, points=10000, voxel_size=0.2, seed=2, baseline_index=1),
+    "config4": dict(submaps=200, pairs=1500, points=20000, voxel_size=0.1, seed=4, baseline_index=3),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -39,63 +53,76 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--submaps", type=int, default=50)
-    ap.add_argument("--pairs", type=int, default=200)
-    ap.add_argument("--points", type=int, default=10000)
-    ap.add_argument("--voxel-size", type=float, default=0.2)
-    ap.add_argument("--no-extras", action="store_true", help="skip solve / TSDF / CPU baseline extras")
+    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config4"],
+                    help="auto: config2 at N = 1 (+ a config4 leg), config4 (strong scaling) at N > 1")
+    ap.add_argument("--submaps", type=int, default=None)
+    ap.add_argument("--pairs", type=int, default=None)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--voxel-size", type=float, default=None)
+    ap.add_argument("--no-extras", action="store_true", help="skip solve / TSDF / CPU baseline / config4 legs")
+    ap.add_argument("--no-config4", action="store_true", help="N = 1: skip the config4 leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     return ap.parse_args()
 
 
+def workload_params(name, args):
+    w = dict(WORKLOADS[name])
+    for k, a in (("submaps", args.submaps), ("pairs", args.pairs), ("points", args.points),
+                 ("voxel_size", args.voxel_size)):
+        if a is not None:
+            w[k] = a
+    w["name"] = name
+    return w
+
+
 # --------------------------------------------------------------------------- workload
-def build_floor(args):
-    """One floor = BASELINE configs[1]: seeded, cached in /tmp (generation is host-side numpy)."""
+def build_scene(w, rank=0, wait_s=1500.0):
+    """Seeded synthetic scene, cached in /tmp (generation is host-side numpy, forked workers: must
+    run before this process touches CUDA).  Under torchrun only rank 0 generates; the others wait
+    for the cache file."""
     from voxgraph_b200 import synth
-    key = "vgx_floor_drift2_s%d_p%d_k%d_v%g.pkl" % (args.submaps, args.pairs, args.points, args.voxel_size)
+    key = "vgx_scene_v3_%s_s%d_p%d_k%d_v%g.pkl" % (w["name"], w["submaps"], w["pairs"], w["points"],
+                                                   w["voxel_size"])
     path = os.path.join("/tmp", key)
-    sc = None
-    if os.path.exists(path):
+
+    def load():
         try:
-            import pickle
             with open(path, "rb") as f:
-                sc = pickle.load(f)
+                return pickle.load(f)
         except Exception:
-            sc = None
-    if sc is None:
-        sc = synth.make_scene(seed=2, n_submaps=args.submaps, n_points=args.points,
-                              voxel_size=args.voxel_size, max_pairs=args.pairs,
-                              trunc=0.6 if abs(args.voxel_size - 0.2) < 1e-9 else None,
-                              drift=(0.03, 0.005, 0.002))
-        try:
-            import pickle
-            tmp = path + ".%d" % os.getpid()
-            with open(tmp, "wb") as f:
-                pickle.dump(sc, f, protocol=4)
-            os.replace(tmp, path)
-        except Exception:
-            pass
+            return None
+
+    sc = load() if os.path.exists(path) else None
+    if sc is not None:
+        return sc
+    if rank != 0:
+        t0 = time.time()
+        while time.time() - t0 < wait_s:
+            if os.path.exists(path):
+                sc = load()
+                if sc is not None:
+                    return sc
+            time.sleep(1.0)
+        raise RuntimeError("rank %d: scene cache %s did not appear" % (rank, path))
+    workers = max(1, min(64, (os.cpu_count() or 2) - 2))
+    sc = synth.make_scene(seed=w["seed"], n_submaps=w["submaps"], n_points=w["points"],
+                          voxel_size=w["voxel_size"], max_pairs=w["pairs"],
+                          trunc=0.6 if abs(w["voxel_size"] - 0.2) < 1e-9 else None,
+                          drift=(0.03, 0.005, 0.002), workers=workers)
+    try:
+        tmp = path + ".%d" % os.getpid()
+        with open(tmp, "wb") as f:
+            pickle.dump(sc, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
     return sc
 
 
-def floors(sc, n_floors):
-    """Weak-scaled problem: n copies of the floor, shifted in the mission frame; submap ids
-    f*S + i. Returns (ids, poses_init, poses_gt, submap_of_id, pairs, odometry)."""
-    S = len(sc.submaps)
-    ids, pinit, pgt, pairs, odo = [], [], [], [], []
-    for f in range(n_floors):
-        shift = np.array([f * (sc.world.size_xy[0] + 30.0), 0.0, 0.0, 0.0])
-        for i in range(S):
-            ids.append(f * S + i)
-            pinit.append(sc.poses_init[i] + shift)
-            pgt.append(sc.poses_gt[i] + shift)
-        pairs += [(f * S + i, f * S + j) for (i, j) in sc.pairs]
-        odo += [(f * S + i, f * S + j, t, y) for (i, j, t, y) in sc.odometry]
-        if f > 0:
-            from voxgraph_b200 import synth
-            t, y = synth.relative_pose(pgt[f * S - 1], pgt[f * S])
-            odo.append((f * S - 1, f * S, t, float(y)))
-    return ids, np.array(pinit), np.array(pgt), pairs, odo
+def scene_problem(sc):
+    """(ids, poses_init, poses_gt, pairs, odometry) of one scene."""
+    ids = list(range(len(sc.submaps)))
+    return ids, np.array(sc.poses_init), np.array(sc.poses_gt), list(sc.pairs), list(sc.odometry)
 
 
 # --------------------------------------------------------------------------- clocks
@@ -142,12 +169,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU reference arm
-def oracle_graph(sc, n_floors, max_residuals=None):
+def oracle_graph(sc, max_residuals=None):
     from oracle import oracle as o
-    ids, pinit, pgt, pairs, odo = floors(sc, n_floors)
-    S = len(sc.submaps)
-    layers = [o.Layer.from_blocks(s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
-              for s in sc.submaps]
+    ids, pinit, pgt, pairs, odo = scene_problem(sc)
+    layers = {}
     g = o.Graph()
     for k, i in enumerate(ids):
         g.add_node(i, pinit[k], constant=(k == 0))
@@ -155,92 +180,297 @@ def oracle_graph(sc, n_floors, max_residuals=None):
     for (i, j, t, y) in odo:
         g.add_relative(i, j, t, y, L)
     R = 0
+
+    def layer(i):
+        if i not in layers:
+            s = sc.submaps[i]
+            layers[i] = o.Layer.from_blocks(s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
+        return layers[i]
     for (i, j) in pairs:
-        a, b = sc.submaps[i % S], sc.submaps[j % S]
-        g.add_registration(i, j, layers[j % S], a.points_xyz, a.points_distance, a.points_weight)
-        g.add_registration(j, i, layers[i % S], b.points_xyz, b.points_distance, b.points_weight)
+        a, b = sc.submaps[i], sc.submaps[j]
+        g.add_registration(i, j, layer(j), a.points_xyz, a.points_distance, a.points_weight)
+        g.add_registration(j, i, layer(i), b.points_xyz, b.points_distance, b.points_weight)
         R += 2 * a.points_xyz.shape[0]
         if max_residuals is not None and R >= max_residuals:
             break
+    g._layers = layers   # keep the layers alive
     return g, o
 
 
-def cpu_reference(sc, args, steps, warmup, budget_s):
-    """Times the restated reference CPU path (oracle) with all host threads on a bounded sample."""
+def cpu_reference(sc, budget_s, reps=5):
+    """Times the restated reference CPU path (oracle; worker threads pinned to distinct cores) on a
+    bounded sample of the workload: median of `reps` evaluations with all host cores and with the
+    reference's own num_threads = 4 (pose_graph.cpp:96)."""
     cores = os.cpu_count() or 1
-    g, o = oracle_graph(sc, 1)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    R_full = 2 * len(sc.pairs) * sc.submaps[0].points_xyz.shape[0]
+    g, o = oracle_graph(sc, max_residuals=min(R_full, 400000))    # probe on <= 400 k residuals
     R = g.num_registration_residuals
+    g.eval(num_threads=cores, want_H=True)                       # pool start-up, first touch
     t = time.time(); g.eval(num_threads=cores, want_H=True); one = time.time() - t
-    # bound the sample: fewer constraints if one full evaluation would blow the budget
-    sample = "all %d registration residuals of the N=1 workload per step" % R
-    if one * (steps + warmup) > budget_s and one > 0:
-        frac = max(0.02, budget_s / (one * (steps + warmup)))
-        g, o = oracle_graph(sc, 1, max_residuals=int(R * frac))
+    per_res = one / max(R, 1)
+    # all-core sample: as many residuals as fit in ~40 % of the budget over `reps` repetitions
+    want = int(min(R_full, max(R, 0.4 * budget_s / (reps * per_res))))
+    if want > R:
+        g, o = oracle_graph(sc, max_residuals=want)
         R = g.num_registration_residuals
-        sample = "first %d registration residuals (%.0f%% of the constraints) of the N=1 workload per step" % (
-            R, 100 * frac)
-    for _ in range(warmup):
         g.eval(num_threads=cores, want_H=True)
-    t0 = time.time()
-    for _ in range(steps):
-        g.eval(num_threads=cores, want_H=True)
-    dt = (time.time() - t0) / steps
-    t4 = time.time(); g.eval(num_threads=min(4, cores), want_H=True); dt4 = time.time() - t4
+    sample = ("all %d registration residuals of the workload per step" % R if R >= R_full else
+              "first %d of %d registration residuals (%.0f%% of the constraints) per step" % (
+                  R, R_full, 100.0 * R / R_full))
+    ts = []
+    for _ in range(reps):
+        t0 = time.time(); g.eval(num_threads=cores, want_H=True); ts.append(time.time() - t0)
+    dt = float(np.median(ts))
+    nt4 = min(4, cores)
+    g.eval(num_threads=nt4, want_H=True)
+    ts4 = []
+    for _ in range(max(3, reps // 2 + 1)):
+        t0 = time.time(); g.eval(num_threads=nt4, want_H=True); ts4.append(time.time() - t0)
+        if sum(ts4) > 0.5 * budget_s:
+            break
+    dt4 = float(np.median(ts4))
     return dict(value=R / dt, unit="residuals/s", cores=cores, kind="port", sample=sample,
-                ms_per_step=dt * 1e3, value_4_threads=R / dt4,
-                note="restated reference (Ceres/voxblox/Eigen absent from the image; see DESIGN.md)")
+                ms_per_step=dt * 1e3, value_4_threads=R / dt4, reps=reps,
+                spread=float((max(ts) - min(ts)) / dt) if dt > 0 else None,
+                note="restated reference (Ceres/voxblox/Eigen absent from the image; see DESIGN.md); "
+                     "median of %d evaluations, worker threads pinned one per core" % reps)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sc = build_floor(args)
+    wname = args.workload if args.workload != "auto" else ("config2" if args.gpus <= 1 else "config4")
+    w = workload_params(wname, args)
+    sc = build_scene(w)
     steps = max(1, args.steps); warmup = max(0, args.warmup)
-    cb = cpu_reference(sc, args, steps, warmup, budget_s=60.0)
+    cb = cpu_reference(sc, budget_s=60.0, reps=max(5, min(steps, 9)))
     line = {"impl": "reference", "metric": "registration_residuals_per_s", "value": cb["value"],
             "unit": "residuals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, sc, 1),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": workload_config(w, sc, args.gpus),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                "value_4_threads", "spread", "note")},
             "e2e": {"value": cb["value"], "unit": "residuals/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
 
 
-def workload_config(args, sc, n_gpus):
-    return {"workload": "BASELINE configs[1]: %d submaps / %d overlapping pairs (x2 mirrored residual "
+def workload_config(w, sc, n_gpus):
+    return {"workload": "BASELINE configs[%d]: %d submaps / %d overlapping pairs (x2 mirrored residual "
                         "blocks) / %d isosurface points per block, %.2f m voxels, 16^3-voxel bricks%s"
-                        % (args.submaps, len(sc.pairs), args.points, args.voxel_size,
-                           "" if n_gpus == 1 else "; x%d floors (weak scaling), constraints sharded over ranks" % n_gpus),
-            "submaps": args.submaps * n_gpus, "pairs": len(sc.pairs) * n_gpus,
-            "points_per_constraint": args.points, "voxel_size": args.voxel_size,
+                        % (w["baseline_index"], len(sc.submaps), len(sc.pairs), w["points"], w["voxel_size"],
+                           "" if n_gpus == 1 else "; every submap resident on all %d GPUs, constraints "
+                           "sharded over the ranks (strong scaling)" % n_gpus),
+            "name": w["name"], "submaps": len(sc.submaps), "pairs": len(sc.pairs),
+            "points_per_constraint": w["points"], "voxel_size": w["voxel_size"],
             "registration_point_type": "isosurface", "sampling_ratio": -1,
             "l2": "inputs (points + reading bricks) exceed the 126 MB L2; no explicit flush in the bracketed region",
-            "parallelism": "pairs sharded x%d, NCCL all-reduce of packed H/g blocks" % n_gpus if n_gpus > 1 else "single GPU"}
+            "parallelism": ("constraints sharded x%d; packed H/g blocks summed by a one-shot NVLink "
+                            "peer-memory all-gather-reduce (CUDA IPC), NCCL all-reduce as fallback" % n_gpus)
+            if n_gpus > 1 else "single GPU"}
 
 
 # --------------------------------------------------------------------------- GPU arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from voxgraph_b200 import api
+class Problem:
+    """One workload resident on this rank's GPU + its pose graph."""
 
+    def __init__(self, ctx, api, sc, id_base=0):
+        self.ctx, self.sc = ctx, sc
+        self.ids, self.pinit, self.pgt, self.pairs, self.odo = scene_problem(sc)
+        self.id_base = id_base
+        t_up = time.time()
+        self.bricks_bytes = 0
+        for k, sid in enumerate(self.ids):
+            s = sc.submaps[sid]
+            ctx.submap_upload(id_base + sid, s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
+            ctx.submap_upload_points(id_base + sid, api.K_ISOSURFACE_POINTS, s.points_xyz,
+                                     s.points_distance, s.points_weight)
+            self.bricks_bytes += s.num_blocks * s.vps ** 3 * 32
+        self.upload_s = time.time() - t_up
+        self.api = api
+        self.n_nodes = len(self.ids)
+        self.build_graph()
+
+    def build_graph(self):
+        api, sc, b = self.api, self.sc, self.id_base
+        pg = api.PoseGraph(self.ctx)
+        for k, sid in enumerate(self.ids):
+            pg.addSubmapNode(api.SubmapNodeConfig(b + sid, self.pinit[k], set_constant=(k == 0)))
+        for (i, j, t, y) in self.odo:
+            pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(b + i, b + j, np.array([*t, y]),
+                                                                          sc.odom_information))
+        for (i, j) in self.pairs:
+            pg.addRegistrationConstraint(api.RegistrationConstraintConfig(b + i, b + j))
+        pg._sync()
+        self.pg = pg
+        self.r_local, self.r_global = self.ctx.graph_num_registration_residuals()
+        self.packed_len = 4 + 20 * self.n_nodes + 16 * len(
+            set((min(a, c), max(a, c)) for (a, c) in list(self.pairs) + [(i, j) for (i, j, _, _) in self.odo]))
+
+    def free(self):
+        for sid in self.ids:
+            self.ctx.submap_free(self.id_base + sid)
+
+
+def measure(P, args, torch, dist, world, stream, want_cpu_pose_check=None):
+    """Device-resident throughput, end-to-end call, roofline split and the pose-graph solve of one
+    resident problem.  Every rank takes part (each evaluation contains the exchange)."""
+    ctx = P.ctx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    out = {}
+    ctx.graph_set_poses(P.pinit)
+    for _ in range(max(args.warmup, 3)):
+        ctx.graph_eval_async()
+    barrier()
+    launches0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.graph_eval_async()
+        e1.record(stream)
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    out["ms_per_step"] = ms_step
+    out["value"] = P.r_global / (ms_step * 1e-3)
+    out["gpu_launches"] = int(ctx.launch_count - launches0)
+
+    # ---- end to end through the public call with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    poses_host = P.pinit.copy()
+    for _ in range(2):
+        ctx.graph_set_poses(poses_host); ctx.graph_eval(P.n_nodes, want_H=False)
+    barrier()
+    t0 = time.time()
+    for k in range(e2e_steps):
+        poses_host[1:, 0] += 1e-6            # new poses every step (H2D inside the timed region)
+        ctx.graph_set_poses(poses_host)
+        ctx.graph_eval(P.n_nodes, want_H=False)   # D2H of cost / gradient / H blocks
+    barrier()
+    e2e_s = max_over_ranks((time.time() - t0) / e2e_steps)
+    out["e2e"] = {"value": P.r_global / e2e_s, "unit": "residuals/s", "ms_per_step": e2e_s * 1e3,
+                  "h2d_bytes_per_step": int(P.n_nodes * 32), "d2h_bytes_per_step": int(P.packed_len * 8),
+                  "call": "vgx_graph_set_poses + vgx_graph_eval (fused reduce mode; host poses in, host "
+                          "cost/gradient/H-blocks out)"}
+    ctx.graph_set_poses(P.pinit)
+
+    # ---- roofline of the dominant kernel (per-kernel CUDA events on the ctx stream)
+    barrier()
+    ctx.profile_reset(); ctx.profile_enable(True)
+    n_prof = max(3, min(args.steps, 10))
+    for _ in range(n_prof):
+        ctx.graph_eval_async()
+    ctx.synchronize()
+    k_ms, k_n = ctx.profile_get(0)
+    o_ms, o_n = ctx.profile_get(5)
+    ctx.profile_enable(False)
+    barrier()
+    kern_ms = k_ms / max(k_n, 1)
+    out["kernel_ms"] = kern_ms
+    out["other_kernels_ms_per_step"] = o_ms / max(k_n, 1)
+
+    # ---- pose-graph solve wall time (second half of the metric)
+    if not args.no_extras:
+        solve = {}
+        for name, kw in (("reference_options", {}),
+                         ("tight", dict(parameter_tolerance=1e-6, function_tolerance=1e-9,
+                                        max_num_iterations=50, max_solver_time_s=60.0))):
+            ms, summ, x = [], None, None
+            for rep in range(3):
+                ctx.graph_set_poses(P.pinit)
+                barrier()
+                t0 = time.time()
+                x, summ = ctx.graph_solve(P.n_nodes, ctx.solver_options(**kw))
+                ms.append((time.time() - t0) * 1e3)
+            d = {"solve_ms": max_over_ranks(float(np.median(ms))), "lm_iterations": summ.iterations,
+                 "successful_steps": summ.num_successful_steps, "residual_evaluations": summ.num_residual_evals,
+                 "termination": summ.termination, "initial_cost": summ.initial_cost,
+                 "final_cost": summ.final_cost,
+                 "unknowns": 4 * (P.n_nodes - 1),
+                 "mean_xy_error_before_m": float(np.abs(P.pinit[:, :2] - P.pgt[:, :2]).mean()),
+                 "mean_xy_error_after_m": float(np.abs(x[:, :2] - P.pgt[:, :2]).mean()),
+                 "options": ("Ceres defaults + parameter_tolerance 3e-3, max_solver_time 4 s (pose_graph.cpp:91-97)"
+                             if not kw else "parameter_tolerance 1e-6, function_tolerance 1e-9, <= 50 iterations")}
+            d["_x"] = x
+            solve[name] = d
+        ctx.graph_set_poses(P.pinit)
+        out["solve"] = solve
+    return out
+
+
+def single_rank_parity(P, torch, dist, world, rank):
+    """N > 1: rank 0 evaluates the FULL problem on its own GPU (communicator suspended, every
+    constraint local) and compares it with the sharded + exchanged result every rank holds."""
+    ctx = P.ctx
+    ctx.graph_set_poses(P.pinit)
+    ok, cost, g, _ = ctx.graph_eval(P.n_nodes, want_H=False)        # sharded, all ranks
+    sums = P.pg.getVisualizationEdgeResiduals()                      # per-constraint (local ones only)
+    res = None
+    dist.barrier()
+    if rank == 0:
+        ctx.comm_suspend(True)
+        ok1, cost1, g1, H1 = ctx.graph_eval(P.n_nodes, want_H=True)
+        ctx.comm_suspend(False)
+    dist.barrier()
+    ok2, cost2, g2, H2 = ctx.graph_eval(P.n_nodes, want_H=True)      # sharded again (tables rebuilt on rank 0)
+    if rank == 0:
+        sg = max(np.abs(g1).max(), 1e-300); sh = max(np.abs(H1).max(), 1e-300)
+        rel = max(abs(cost2 - cost1) / max(abs(cost1), 1e-300), float(np.abs(g2 - g1).max() / sg),
+                  float(np.abs(H2 - H1).max() / sh))
+        res = {"parity_vs_single_rank": rel, "cost_equal": bool(abs(cost2 - cost1) <= 1e-12 * abs(cost1)),
+               "cost_sharded": cost2, "cost_single_rank": cost1, "tolerance": 1e-12,
+               "how": "rank 0 re-evaluates all constraints on one GPU (vgx_comm_suspend) and compares cost, "
+                      "gradient and every H block with the exchanged result: max relative error"}
+    return res
+
+
+def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = world
+    wname = args.workload if args.workload != "auto" else ("config2" if world == 1 else "config4")
+    w_main = workload_params(wname, args)
+    want_c4_leg = (world == 1 and wname == "config2" and not args.no_extras and not args.no_config4)
+    # scenes first: generation forks worker processes and must precede CUDA initialisation
+    sc = build_scene(w_main, rank)
+    w_c4 = workload_params("config4", args) if want_c4_leg else None
+    sc_c4 = None
+    if want_c4_leg:
+        try:
+            sc_c4 = build_scene(w_c4, rank)
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write("config4 leg skipped: %r\n" % (e,))
+
+    import torch
+    import torch.distributed as dist
+    from voxgraph_b200 import api
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_gpus = world
-
-    sc = build_floor(args)
-    ids, pinit, pgt, pairs, odo = floors(sc, n_gpus)
-    S = len(sc.submaps)
 
     ctx = api.Context(local_rank)
     comm_kind = None
@@ -263,92 +493,17 @@ def run_b200(args):
         else:
             comm_kind = "ncclAllReduce"
 
-    t_up = time.time()
-    bricks_bytes = 0
-    for k, sid in enumerate(ids):
-        s = sc.submaps[sid % S]
-        ctx.submap_upload(sid, s.voxel_size, s.vps, s.block_idx, s.distance, s.weight)
-        ctx.submap_upload_points(sid, api.K_ISOSURFACE_POINTS, s.points_xyz, s.points_distance,
-                                 s.points_weight)
-        bricks_bytes += s.num_blocks * s.vps ** 3 * 32
-    upload_s = time.time() - t_up
-
-    pg = api.PoseGraph(ctx)
-    for k, sid in enumerate(ids):
-        pg.addSubmapNode(api.SubmapNodeConfig(sid, pinit[k], set_constant=(k == 0)))
-    for (i, j, t, y) in odo:
-        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(i, j, np.array([*t, y]),
-                                                                      sc.odom_information))
-    for (i, j) in pairs:
-        pg.addRegistrationConstraint(api.RegistrationConstraintConfig(i, j))
-    pg._sync()
-    r_local, r_global = ctx.graph_num_registration_residuals()
-    n_nodes = len(ids)
-
     stream = torch.cuda.ExternalStream(ctx.stream_ptr)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput: K steps in one bracket
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_load0 = time.time()
-    for _ in range(max(args.warmup, 3)):
-        ctx.graph_eval_async()
-    barrier()
-    launches0 = ctx.launch_count
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            ctx.graph_eval_async()
-        e1.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = r_global / (ms_step * 1e-3)
+    P = Problem(ctx, api, sc)
+    M = measure(P, args, torch, dist, world, stream)
+    ms_step = M["ms_per_step"]
 
-    # ---------------- end to end through the public call with host buffers
-    e2e_steps = max(3, min(args.steps, 10))
-    poses_host = pinit.copy()
-    for _ in range(2):
-        ctx.graph_set_poses(poses_host); ctx.graph_eval(n_nodes, want_H=False)
-    barrier()
-    t0 = time.time()
-    for k in range(e2e_steps):
-        poses_host[1:, 0] += 1e-6            # new poses every step (H2D inside the timed region)
-        ctx.graph_set_poses(poses_host)
-        ok, cost, g, _ = ctx.graph_eval(n_nodes, want_H=False)   # D2H of cost / gradient / H blocks
-    barrier()
-    e2e_s = (time.time() - t0) / e2e_steps
+    parity = None
     if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    packed_len = 4 + 20 * n_nodes + 16 * len(set((min(a, b), max(a, b)) for (a, b) in
-                                                [(i, j) for (i, j) in pairs] + [(i, j) for (i, j, _, _) in odo]))
-    e2e = {"value": r_global / e2e_s, "unit": "residuals/s", "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": int(n_nodes * 32), "d2h_bytes_per_step": int(packed_len * 8),
-           "call": "vgx_graph_set_poses + vgx_graph_eval (fused reduce mode; host poses in, host cost/gradient/H-blocks out)"}
+        parity = single_rank_parity(P, torch, dist, world, rank)
 
-    # ---------------- roofline of the dominant kernel (per-kernel CUDA events on the ctx stream)
-    ctx.profile_reset(); ctx.profile_enable(True)
-    for _ in range(max(3, min(args.steps, 10))):
-        ctx.graph_eval_async()
-    ctx.synchronize()
-    k_ms, k_n = ctx.profile_get(0)
-    o_ms, o_n = ctx.profile_get(5)
-    ctx.profile_enable(False)
     # keep the GPU under the same evaluation load long enough for nvidia-smi (100 ms period) to
     # see it: the clocks line covers warm-up + the timed bracket + e2e + this sustained tail
     # (iteration count derived from the rank-reduced step time: every rank must issue the same
@@ -361,148 +516,177 @@ def run_b200(args):
     ctx.synchronize()
     clocks = sampler.stop(t_load0, time.time()) if sampler else None
     if clocks is not None:
-        clocks["window"] = "warm-up + timed bracket + e2e + 0.6 s of the same evaluation loop"
+        clocks["window"] = "upload + warm-up + timed bracket + e2e + solve + 0.6 s of the same evaluation loop"
 
-    kern_ms = k_ms / max(k_n, 1)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback 6.65 TB/s (MEASURED_PEAKS.json absent)"
-    achieved = r_local * ALGO_BYTES_PER_RESIDUAL / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "reg_reduce_kernel<true>", "achieved": achieved, "peak": peak,
+
+    def roofline_of(Pm, Mm):
+        achieved = Pm.r_local * ALGO_BYTES_PER_RESIDUAL / (Mm["kernel_ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "reg_reduce_kernel<true>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_residual": ALGO_BYTES_PER_RESIDUAL,
-                "residuals_per_launch": int(r_local), "kernel_ms": kern_ms,
-                "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
-                "other_kernels_ms_per_step": (o_ms / max(k_n, 1))}
+                "residuals_per_launch": int(Pm.r_local), "kernel_ms": Mm["kernel_ms"],
+                "kernel_share_of_step": Mm["kernel_ms"] / Mm["ms_per_step"] if Mm["ms_per_step"] > 0 else None,
+                "other_kernels_ms_per_step": Mm["other_kernels_ms_per_step"]}
+
+    roofline = roofline_of(P, M)
     prof_traffic = os.path.join(ROOT, "profiles", "reg_reduce_traffic.json")
-    if os.path.exists(prof_traffic):
+    if os.path.exists(prof_traffic) and wname == "config2":
         try:
             roofline["traffic"] = json.load(open(prof_traffic)).get("dram_bytes_per_launch")
         except Exception:
             pass
 
+    e2e = M["e2e"]
     extras = {}
-    if not args.no_extras:
-        # ---------------- pose-graph solve wall time (second half of the metric)
-        def gpu_solve(**kw):
-            ms, summ, x = [], None, None
-            for rep in range(3):
-                ctx.graph_set_poses(pinit)
-                barrier()
-                t0 = time.time()
-                x, summ = ctx.graph_solve(n_nodes, ctx.solver_options(**kw))
-                ms.append((time.time() - t0) * 1e3)
-            return float(np.median(ms)), summ, x
-        err0 = float(np.abs(pinit[:, :2] - pgt[:, :2]).mean())
-        extras["solve"] = {}
-        for name, kw in (("reference_options", {}),
-                         ("tight", dict(parameter_tolerance=1e-6, function_tolerance=1e-9,
-                                        max_num_iterations=50, max_solver_time_s=60.0))):
-            ms, summ, x = gpu_solve(**kw)
-            # kernel-time split of one more solve (per-kernel events; not used for solve_ms)
-            ctx.graph_set_poses(pinit); ctx.profile_reset(); ctx.profile_enable(True)
-            ctx.graph_solve(n_nodes, ctx.solver_options(**kw))
-            lm_ms, lm_n = ctx.profile_get(4); rk_ms, rk_n = ctx.profile_get(0); ot_ms, _ = ctx.profile_get(5)
-            ctx.profile_enable(False)
-            extras["solve"][name] = {
-                "kernel_ms_split": {"lm_cholesky_step_decide": lm_ms, "registration_reduce": rk_ms,
-                                    "pose_setup_assemble": ot_ms},
-                "solve_ms": ms, "lm_iterations": summ.iterations,
-                "successful_steps": summ.num_successful_steps, "residual_evaluations": summ.num_residual_evals,
-                "termination": summ.termination, "initial_cost": summ.initial_cost,
-                "final_cost": summ.final_cost, "mean_xy_error_before_m": err0,
-                "mean_xy_error_after_m": float(np.abs(x[:, :2] - pgt[:, :2]).mean()),
-                "options": ("Ceres defaults + parameter_tolerance 3e-3, max_solver_time 4 s (pose_graph.cpp:91-97)"
-                            if not kw else "parameter_tolerance 1e-6, function_tolerance 1e-9, <= 50 iterations")}
-            extras["solve"][name]["_x"] = x
-        if rank == 0:
-            # ---------------- TSDF integration (HP1), configs[2]-shaped scan, rank 0 only
-            from voxgraph_b200 import synth
-            wpose = np.array([sc.poses_gt[0][0], sc.poses_gt[0][1], 1.2, 0.3])
-            pts = synth.lidar_scan(sc.world, wpose, n_beams=64, n_azimuth=1024, seed=3, miss_range=40.0)
-            T = synth.pose_to_T([0, 0, 0, 0])
-            from oracle import oracle as o
-            extras["tsdf"] = {"rays": int(pts.shape[0]), "scan": "64x1024 LiDAR, 0.20 m voxels, trunc 0.6 m, max ray 16 m",
-                              "algorithmic_bytes_per_update": ALGO_BYTES_PER_TSDF_UPDATE}
-            for name, kw in (("simple_atomic", dict(mode=0, deterministic=0)),
-                             ("simple_ray_ordered", dict(mode=0, deterministic=1)),
-                             ("fast", dict(mode=1))):
-                cfg = ctx.tsdf_config(**kw)
-                ctx.submap_create(10 ** 6, 0.2, 16, 8192)
-                ctx.tsdf_integrate(10 ** 6, T, pts, cfg)      # allocates the blocks (warm-up)
-                ctx.profile_reset(); ctx.profile_enable(True)
-                reps = 3
-                for _ in range(reps):
-                    st = ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
-                ims, inn = ctx.profile_get(2); ams, ann = ctx.profile_get(3)
-                ctx.profile_enable(False)
-                t0 = time.time()
-                for _ in range(reps):
-                    st = ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
-                wall = (time.time() - t0) / reps
-                kms = ims / reps
-                # CPU: the restated reference integrator, single-threaded (the oracle is serial)
-                lay = o.Layer(0.2, 16)
-                oc = o.tsdf_config(mode=kw["mode"])
-                o.tsdf_integrate(lay, oc, T, pts)
-                tc = time.time(); so = o.tsdf_integrate(lay, oc, T, pts); cpu_s = time.time() - tc
-                extras["tsdf"][name] = {
-                    "voxel_updates_per_scan": int(st.voxel_updates), "rays_cast": int(st.rays_cast),
-                    "integrate_kernels_ms": kms, "allocate_kernel_ms": ams / max(ann, 1),
-                    "updates_per_s_kernels": st.voxel_updates / (kms * 1e-3),
-                    "scan_ms_e2e_host_points": wall * 1e3,
-                    "updates_per_s_e2e": st.voxel_updates / wall,
-                    "achieved_gbs": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9,
-                    "frac_of_hbm_peak": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9 / peak,
-                    "cpu_reference_scan_ms_1_thread": cpu_s * 1e3,
-                    "cpu_reference_updates_per_s": so.voxel_updates / cpu_s}
-                ctx.submap_free(10 ** 6)
-
     cpu = None
-    if rank == 0 and n_gpus == 1 and not args.no_extras:
-        cpu = cpu_reference(sc, args, steps=3, warmup=1, budget_s=args.cpu_seconds)
-        if "solve" in extras:
-            # the restated reference's CPU solve of the same problem with the same options
+    if "solve" in M:
+        extras["solve"] = M["solve"]
+    if rank == 0 and not args.no_extras:
+        # ---------------- CPU baseline (pinned threads, median) + the restated reference's solve
+        cpu = cpu_reference(sc, budget_s=args.cpu_seconds)
+        if world == 1 and "solve" in M:
             from oracle import oracle as o
             nt = min(4, os.cpu_count() or 1)   # pose_graph.cpp:96 num_threads = 4
             for name, kw in (("reference_options", {}),
                              ("tight", dict(parameter_tolerance=1e-6, function_tolerance=1e-9,
                                             max_num_iterations=50, max_solver_time_s=60.0))):
                 try:
-                    g, _ = oracle_graph(sc, 1)
+                    g, _ = oracle_graph(sc)
                     rc, so = g.solve(o.solver_options(num_threads=nt, **kw))
-                    d = extras["solve"][name]
+                    d = M["solve"][name]
                     d["cpu_reference_solve_ms"] = so.total_time_s * 1e3
                     d["cpu_reference_iterations"] = so.iterations
                     d["cpu_reference_final_cost"] = so.final_cost
                     d["cpu_reference_threads"] = nt
                     d["max_pose_diff_vs_cpu_reference"] = float(np.abs(d["_x"] - g.poses()).max())
                 except Exception as e:  # pragma: no cover
-                    extras["solve"][name]["cpu_reference_error"] = repr(e)
-    for d in extras.get("solve", {}).values():
+                    M["solve"][name]["cpu_reference_error"] = repr(e)
+    if "solve" in M:
+        ref_opts = M["solve"]["reference_options"]
+        # the second half of the metric rides in a dict the driver keeps
+        e2e["solve_ms"] = ref_opts["solve_ms"]
+        e2e["lm_iterations"] = ref_opts["lm_iterations"]
+        e2e["solve_unknowns"] = ref_opts["unknowns"]
+        e2e["solve_final_cost"] = ref_opts["final_cost"]
+        e2e["solve_ms_tight"] = M["solve"]["tight"]["solve_ms"]
+        e2e["lm_iterations_tight"] = M["solve"]["tight"]["lm_iterations"]
+        if "max_pose_diff_vs_cpu_reference" in ref_opts:
+            e2e["max_pose_diff_vs_cpu_reference"] = ref_opts["max_pose_diff_vs_cpu_reference"]
+            e2e["cpu_reference_solve_ms"] = ref_opts["cpu_reference_solve_ms"]
+    if parity is not None:
+        e2e["parity_vs_single_rank"] = parity["parity_vs_single_rank"]
+        e2e["cost_equal"] = parity["cost_equal"]
+        roofline["parity_vs_single_rank"] = parity["parity_vs_single_rank"]
+        extras["parity"] = parity
+
+    # ---------------- TSDF integration (HP1), configs[2]-shaped scan, rank 0, N = 1 only
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras["tsdf"] = tsdf_leg(ctx, sc, peak)
+            e2e["tsdf_fast_updates_per_s_e2e"] = extras["tsdf"]["fast"]["updates_per_s_e2e"]
+            e2e["tsdf_ray_ordered_updates_per_s_e2e"] = extras["tsdf"]["simple_ray_ordered"]["updates_per_s_e2e"]
+        except Exception as e:  # pragma: no cover
+            extras["tsdf"] = {"error": repr(e)}
+
+    # ---------------- config4 leg at N = 1 (the strong-scaling curve's own first point)
+    if sc_c4 is not None:
+        try:
+            P.free()
+            P4 = Problem(ctx, api, sc_c4, id_base=100000)
+            M4 = measure(P4, args, torch, dist, world, stream)
+            c4 = {"workload": workload_config(w_c4, sc_c4, 1)["workload"], "value": M4["value"],
+                  "unit": "residuals/s", "ms_per_step": M4["ms_per_step"],
+                  "residuals_per_step": int(P4.r_global), "e2e_value": M4["e2e"]["value"],
+                  "upload_s": P4.upload_s}
+            if "solve" in M4:
+                c4["solve_ms"] = M4["solve"]["reference_options"]["solve_ms"]
+                c4["lm_iterations"] = M4["solve"]["reference_options"]["lm_iterations"]
+                c4["solve_unknowns"] = M4["solve"]["reference_options"]["unknowns"]
+                c4["solve_ms_tight"] = M4["solve"]["tight"]["solve_ms"]
+            e2e["config4"] = c4
+            r4 = roofline_of(P4, M4)
+            roofline["config4"] = {k: r4[k] for k in ("achieved", "frac", "kernel_ms", "residuals_per_launch",
+                                                      "kernel_share_of_step")}
+            P4.free()
+        except Exception as e:  # pragma: no cover
+            e2e["config4"] = {"error": repr(e)}
+    for d in M.get("solve", {}).values():
         d.pop("_x", None)
 
     if rank == 0:
-        line = {"metric": "registration_residuals_per_s", "value": value, "unit": "residuals/s",
+        if parity is not None and not (parity["parity_vs_single_rank"] <= 1e-12):
+            sys.stderr.write("PARITY FAILURE vs single rank: %r\n" % (parity,))
+        line = {"metric": "registration_residuals_per_s", "value": M["value"], "unit": "residuals/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if wname == "config4" else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, sc, n_gpus),
-                "residuals_per_step": int(r_global), "gpu_launches": int(launches),
+                "config": workload_config(w_main, sc, n_gpus),
+                "residuals_per_step": int(P.r_global), "gpu_launches": M["gpu_launches"],
                 "clocks": clocks, "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample",
-                                                       "value_4_threads", "note")} if cpu else None),
-                "collective": comm_kind, "upload_s": upload_s, "resident_bytes": {"points": int(r_global // max(n_gpus, 1) * 20),
-                                                         "reading_bricks_view": int(bricks_bytes)}}
+                                                       "value_4_threads", "spread", "note")} if cpu else None),
+                "collective": comm_kind, "upload_s": P.upload_s,
+                "resident_bytes": {"points": int(P.r_global // 2 * 20 // max(len(sc.pairs), 1) * len(sc.submaps)),
+                                   "reading_bricks_view": int(P.bricks_bytes)}}
         line.update(extras)
         _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
+    failed = parity is not None and not (parity["parity_vs_single_rank"] <= 1e-12)
     if world > 1:
         dist.barrier()      # tear the peer mappings down together
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        sys.exit(3)
+
+
+def tsdf_leg(ctx, sc, peak):
+    """HP1 on a configs[2]-shaped scan (64 x 1024 LiDAR): the integrator the reference runs (Fast) and
+    the ray-ordered Simple path, next to the restated reference on the host."""
+    from oracle import oracle as o
+    from voxgraph_b200 import synth
+    wpose = np.array([sc.poses_gt[0][0], sc.poses_gt[0][1], 1.2, 0.3])
+    pts = synth.lidar_scan(sc.world, wpose, n_beams=64, n_azimuth=1024, seed=3, miss_range=40.0)
+    T = synth.pose_to_T([0, 0, 0, 0])
+    out = {"rays": int(pts.shape[0]), "scan": "64x1024 LiDAR, 0.20 m voxels, trunc 0.6 m, max ray 16 m",
+           "algorithmic_bytes_per_update": ALGO_BYTES_PER_TSDF_UPDATE}
+    for name, kw in (("simple_ray_ordered", dict(mode=0)), ("fast", dict(mode=1))):
+        cfg = ctx.tsdf_config(**kw)
+        ctx.submap_create(10 ** 6, 0.2, 16, 8192)
+        ctx.tsdf_integrate(10 ** 6, T, pts, cfg)      # allocates the blocks (warm-up)
+        ctx.profile_reset(); ctx.profile_enable(True)
+        reps = 3
+        for _ in range(reps):
+            st = ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
+        ims, inn = ctx.profile_get(2); ams, ann = ctx.profile_get(3)
+        ctx.profile_enable(False)
+        t0 = time.time()
+        for _ in range(reps):
+            st = ctx.tsdf_integrate(10 ** 6, T, pts, cfg)
+        wall = (time.time() - t0) / reps
+        kms = (ims + ams) / reps
+        lay = o.Layer(0.2, 16)
+        oc = o.tsdf_config(mode=kw["mode"])
+        o.tsdf_integrate(lay, oc, T, pts)
+        tc = time.time(); so = o.tsdf_integrate(lay, oc, T, pts); cpu_s = time.time() - tc
+        out[name] = {
+            "voxel_updates_per_scan": int(st.voxel_updates), "rays_cast": int(st.rays_cast),
+            "kernels_ms": kms,
+            "updates_per_s_kernels": st.voxel_updates / (kms * 1e-3),
+            "scan_ms_e2e_host_points": wall * 1e3,
+            "updates_per_s_e2e": st.voxel_updates / wall,
+            "achieved_gbs": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9 / peak,
+            "cpu_reference_scan_ms_1_thread": cpu_s * 1e3,
+            "cpu_reference_updates_per_s_1_thread": so.voxel_updates / cpu_s}
+        ctx.submap_free(10 ** 6)
+    return out
 
 
 def main():

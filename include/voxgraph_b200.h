@@ -72,6 +72,37 @@ int vgx_submap_create(vgx_ctx* ctx, uint32_t submap_id, float voxel_size, int vo
 /* VoxgraphSubmap::finishSubmap (voxgraph_submap.cpp:84-107), device part: freezes the
  * layer and builds the registration view of the bricks. */
 int vgx_submap_finish(vgx_ctx* ctx, uint32_t submap_id);
+/* The rest of finishSubmap (voxgraph_submap.cpp:84-107) on the device, so that a submap integrated
+ * on the GPU never leaves it between HP1 and HP2:
+ *   findRelevantVoxelIndices (cpp:144-201)  -> registration points of type VGX_POINTS_VOXELS
+ *   findIsosurfaceVertices   (cpp:203-243)  -> registration points of type VGX_POINTS_ISOSURFACE
+ *                                              (+ the isosurface block list overlapsWith uses)
+ *   getSubmapFrameSurfaceObb (cpp:280-324)
+ * Order of the points: blocks in allocation order, voxels in linear order, cube edges 0..11 (the
+ * reference iterates a hash map; see oracle/vg_oracle.h vgo_find_isosurface_vertices). */
+typedef struct vgx_registration_filter {   /* VoxgraphSubmap::Config::RegistrationFilter (h:26-30) */
+  double min_voxel_weight;                 /* 1 */
+  double max_voxel_distance;               /* 0.3 */
+  int use_esdf_distance;                   /* reference default true; 0 here = TSDF distance */
+} vgx_registration_filter;
+void vgx_registration_filter_default(vgx_registration_filter* f);
+/* On a finished submap (uploaded or integrated). filter may be NULL (defaults). */
+int vgx_submap_extract_points(vgx_ctx* ctx, uint32_t submap_id, const vgx_registration_filter* filter);
+/* vgx_submap_finish + vgx_submap_extract_points. */
+int vgx_submap_finish_ex(vgx_ctx* ctx, uint32_t submap_id, const vgx_registration_filter* filter);
+int vgx_submap_num_points(vgx_ctx* ctx, uint32_t submap_id, int point_type, int* n);
+/* Copies the registration points back (inspection / parity); any output may be NULL. */
+int vgx_submap_download_points(vgx_ctx* ctx, uint32_t submap_id, int point_type, int max_n,
+                               float* xyz /* n x 3 */, float* distance, float* weight, int* n);
+/* Submap-frame surface OBB; VGX_ZERO_WEIGHT when no voxel qualified (box stays +-inf). */
+int vgx_submap_surface_obb(vgx_ctx* ctx, uint32_t submap_id, float obb_min[3], float obb_max[3]);
+/* PoseGraphInterface::updateOverlappingSubmapList (pose_graph_interface.cpp:109-147) over
+ * VoxgraphSubmap::overlapsWith (voxgraph_submap.cpp:245-278): mission-frame surface-AABB rejection,
+ * then "any isosurface block centre of the first submap lands in an allocated block of the second",
+ * for every i < j of the list.  poses: n x 7 = T_mission_submap [qw qx qy qz tx ty tz] (float, as
+ * cblox stores them).  Needs vgx_submap_extract_points on every submap.  pairs: 2 ids per pair. */
+int vgx_find_overlapping_pairs(vgx_ctx* ctx, int n, const uint32_t* submap_ids, const float* poses,
+                               int max_pairs, uint32_t* pairs, int* n_pairs);
 int vgx_submap_free(vgx_ctx* ctx, uint32_t submap_id);
 int vgx_submap_block_count(vgx_ctx* ctx, uint32_t submap_id, int* n_blocks);
 /* Layer geometry and state (any output may be NULL). */
@@ -254,6 +285,11 @@ int vgx_comm_destroy(vgx_ctx* ctx);
  * (bit-identical on all ranks). export: allocate + get the 64-byte IPC handle; import: map
  * the peers (handles = nranks x 64 bytes, own entry ignored). Works with or without
  * vgx_comm_init; when both are set the peer path is used. */
+/* Self-check of the sharded evaluation: while suspended (on = 1) the context behaves as a
+ * single-rank context - it evaluates EVERY constraint locally and skips the exchange - so a rank
+ * can compare the all-reduced result with the full problem computed on one GPU (all submaps are
+ * replicated anyway).  Local to the calling rank; on = 0 restores the rank layout. */
+int vgx_comm_suspend(vgx_ctx* ctx, int on);
 int vgx_comm_p2p_export(vgx_ctx* ctx, uint64_t capacity_doubles, uint8_t handle[64]);
 int vgx_comm_p2p_import(vgx_ctx* ctx, int nranks, int rank, const uint8_t* handles);
 

@@ -182,6 +182,9 @@ def lib():
     L.vgo_graph_registration_costs.argtypes = [vp, f64p]
     L.vgo_graph_solve.argtypes = [vp, C.POINTER(SolverOptions), C.POINTER(SolverSummary)]
     L.vgo_find_relevant_voxels.argtypes = [vp, C.c_double, C.c_double, f32p, f32p, f32p, C.c_int]
+    L.vgo_find_isosurface_vertices.argtypes = [vp, C.c_double, f32p, f32p, f32p, C.c_int, i32p, C.c_int,
+                                               C.POINTER(C.c_int)]
+    L.vgo_interp_voxel.argtypes = [vp, f32p, f32p, f32p]
     L.vgo_surface_obb.argtypes = [vp, C.c_double, C.c_double, f32p, f32p]
     L.vgo_aabb_from_obb_and_pose.argtypes = [f32p, f32p, f32p, f32p, f32p]
     L.vgo_submaps_overlap.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_float, vp]
@@ -503,6 +506,25 @@ def find_relevant_voxels(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):
     lib().vgo_find_relevant_voxels(layer._h, float(min_voxel_weight), float(max_voxel_distance),
                                    _p(xyz, C.c_float), _p(d, C.c_float), _p(w, C.c_float), n)
     return xyz, d, w
+
+
+def find_isosurface_vertices(layer, min_voxel_weight=1.0):
+    """findIsosurfaceVertices -> (xyz (n,3), distance (n,), weight (n,), isosurface_blocks (m,3))."""
+    cap = max(1, layer.num_blocks) * 4096
+    xyz = np.zeros((cap, 3), np.float32); d = np.zeros(cap, np.float32); w = np.zeros(cap, np.float32)
+    blk = np.zeros((max(1, layer.num_blocks) * 8, 3), np.int32); nb = C.c_int(0)
+    n = lib().vgo_find_isosurface_vertices(layer._h, float(min_voxel_weight), _p(xyz, C.c_float),
+                                           _p(d, C.c_float), _p(w, C.c_float), cap, _p(blk, C.c_int32),
+                                           blk.shape[0], C.byref(nb))
+    assert n <= cap and nb.value <= blk.shape[0]
+    return xyz[:n].copy(), d[:n].copy(), w[:n].copy(), blk[:nb.value].copy()
+
+
+def interp_voxel(layer, pos):
+    """Interpolator::getVoxel(pos, interpolate=True) -> (ok, distance, weight)."""
+    p = f32(pos); d = C.c_float(0); w = C.c_float(0)
+    ok = lib().vgo_interp_voxel(layer._h, _p(p, C.c_float), C.byref(d), C.byref(w))
+    return bool(ok), d.value, w.value
 
 
 def surface_obb(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):

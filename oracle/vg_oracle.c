@@ -13,6 +13,7 @@
 #include <string.h>
 #include <time.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdatomic.h>
 #include <stdint.h>
 
@@ -643,9 +644,34 @@ static struct {
 } g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
             NULL, 0, 0, 0, 0, NULL, NULL};
 
+/* Worker t is pinned to the t-th CPU of the process's affinity mask (round robin): without it
+ * the evaluation time of the same problem varied 5x between runs on the shared GPU hosts
+ * (threads migrating between sockets / sharing cores).  VGO_PIN=0 disables it. */
+static void pool_pin_self(int id) {
+  const char* e = getenv("VGO_PIN");
+  if (e && e[0] == '0') return;
+  cpu_set_t all;
+  CPU_ZERO(&all);
+  if (sched_getaffinity(0, sizeof(all), &all) != 0) return;
+  const int n = CPU_COUNT(&all);
+  if (n <= 0) return;
+  int want = id % n, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c) {
+    if (!CPU_ISSET(c, &all)) continue;
+    if (seen++ == want) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(c, &one);
+      pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      return;
+    }
+  }
+}
+
 static void* pool_main(void* p) {
   const int id = (int)(intptr_t)p;
   unsigned long seen = 0;
+  pool_pin_self(id);
   pthread_mutex_lock(&g_pool.mu);
   for (;;) {
     while (g_pool.generation == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
@@ -1048,6 +1074,139 @@ int vgo_find_relevant_voxels(const vgo_layer* l, double min_w, double max_d, flo
       }
     }
   }
+  return n;
+}
+
+/* Interpolator::getVoxel(pos, &voxel, interpolate = true) -> getInterpVoxel: distance and weight
+ * are each q * (interp_table * values^T) with the B1 table of the cost function (A.3) */
+int vgo_interp_voxel(const vgo_layer* l, const float pos[3], float* distance, float* weight) {
+  int32_t bb[3], bv[3], slots[8], lin[8];
+  float d[8], q[8], w[8];
+  if (!vgo_interp_voxels_and_q(l, pos, bb, bv, slots, lin, d, q)) return 0;
+  for (int i = 0; i < 8; ++i) w[i] = l->weight[(size_t)slots[i] * l->vox_per_block + lin[i]];
+  const float* v[2] = {d, w};
+  float out[2];
+  for (int k = 0; k < 2; ++k) {
+    const float* x = v[k];
+    float a[8];
+    a[0] = x[0];
+    a[1] = -x[0] + x[4];
+    a[2] = -x[0] + x[2];
+    a[3] = -x[0] + x[1];
+    a[4] = x[0] - x[2] - x[4] + x[6];
+    a[5] = x[0] - x[1] - x[2] + x[3];
+    a[6] = x[0] - x[1] - x[4] + x[5];
+    a[7] = -x[0] + x[1] + x[2] - x[3] + x[4] - x[5] - x[6] + x[7];
+    float r = q[0] * a[0];
+    for (int i = 1; i < 8; ++i) r = r + q[i] * a[i];
+    out[k] = r;
+  }
+  *distance = out[0];
+  *weight = out[1];
+  return 1;
+}
+
+/* marching cubes corner offsets and edge end points (voxblox marching_cubes.h) */
+static const int kCubeOffset[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
+                                      {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static const int kEdgePairs[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6},
+                                      {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+
+int vgo_find_isosurface_vertices(const vgo_layer* l, double min_w, float* xyz, float* distance,
+                                 float* weight, int max_n, int32_t* iso_blocks, int max_blocks,
+                                 int* n_blocks_out) {
+  const int vps = l->vps;
+  const float min_weight = (float)min_w; /* cpp:211-212 static_cast<float> */
+  /* createConnectedMesh: threshold_inv = 1. / double(float threshold), threshold = 0.5 * voxel_size */
+  const float threshold = (float)(0.5 * (double)l->voxel_size);
+  const double threshold_inv = 1.0 / (double)threshold;
+  /* bucket set: open addressing on the three int64 bucket coordinates */
+  size_t cap = 1024;
+  while (cap < (size_t)l->n_blocks * 4096u) cap <<= 1;
+  int64_t* keys = (int64_t*)malloc(sizeof(int64_t) * 3 * cap);
+  uint8_t* used = (uint8_t*)calloc(cap, 1);
+  int n = 0, nb = 0;
+  for (int b = 0; b < l->n_blocks; ++b) {
+    const int32_t* bi = l->idx + 3 * b;
+    const float origin[3] = {(float)bi[0] * l->block_size, (float)bi[1] * l->block_size,
+                             (float)bi[2] * l->block_size};
+    for (int lin = 0; lin < l->vox_per_block; ++lin) {
+      const int v[3] = {lin % vps, (lin / vps) % vps, lin / (vps * vps)};
+      /* cube origin coordinates = voxel centre (Block::computeCoordinatesFromVoxelIndex) */
+      const float coords[3] = {origin[0] + ((float)v[0] + 0.5f) * l->voxel_size,
+                               origin[1] + ((float)v[1] + 0.5f) * l->voxel_size,
+                               origin[2] + ((float)v[2] + 0.5f) * l->voxel_size};
+      float sdf[8], cc[8][3];
+      int all = 1;
+      for (int i = 0; i < 8 && all; ++i) {
+        int cv[3], cb[3];
+        for (int a = 0; a < 3; ++a) {
+          cv[a] = v[a] + kCubeOffset[i][a];
+          cb[a] = bi[a];
+          if (cv[a] >= vps) { cv[a] -= vps; cb[a] += 1; }
+        }
+        const int32_t cbi[3] = {cb[0], cb[1], cb[2]};
+        const int slot = vgo_layer_find_block(l, cbi);
+        if (slot < 0) { all = 0; break; }
+        const size_t o = (size_t)slot * l->vox_per_block + cv[0] + vps * (cv[1] + vps * cv[2]);
+        /* utils::getSdfIfValid: weight <= min_weight -> invalid */
+        if (l->weight[o] <= min_weight) { all = 0; break; }
+        sdf[i] = l->distance[o];
+        /* corner_coords = coords + cube_coord_offsets (offset = index offset * voxel_size) */
+        for (int a = 0; a < 3; ++a) cc[i][a] = coords[a] + (float)kCubeOffset[i][a] * l->voxel_size;
+      }
+      if (!all) continue;
+      for (int e = 0; e < 12; ++e) {
+        const int e0 = kEdgePairs[e][0], e1 = kEdgePairs[e][1];
+        const float s1 = sdf[e0], s2 = sdf[e1];
+        if (!((s1 < 0 && s2 >= 0) || (s1 >= 0 && s2 < 0))) continue;
+        /* MarchingCubes::interpolateVertex */
+        float p[3];
+        const float diff = s1 - s2;
+        if (fabsf(diff) >= 1e-6f) {
+          const float t = s1 / diff;
+          for (int a = 0; a < 3; ++a) p[a] = cc[e0][a] + t * (cc[e1][a] - cc[e0][a]);
+        } else {
+          for (int a = 0; a < 3; ++a) p[a] = 0.5f * (cc[e0][a] + cc[e1][a]);
+        }
+        /* createConnectedMesh: bucket = round(double(vertex) * threshold_inv) */
+        int64_t k3[3];
+        for (int a = 0; a < 3; ++a) k3[a] = (int64_t)llround((double)p[a] * threshold_inv);
+        uint64_t h = any_index_hash(k3[0], k3[1], k3[2]);
+        h ^= h >> 29;
+        size_t pos = (size_t)(h * 0x9E3779B97F4A7C15ull) & (cap - 1);
+        int dup = 0;
+        while (used[pos]) {
+          if (keys[3 * pos] == k3[0] && keys[3 * pos + 1] == k3[1] && keys[3 * pos + 2] == k3[2]) { dup = 1; break; }
+          pos = (pos + 1) & (cap - 1);
+        }
+        if (dup) continue;
+        used[pos] = 1;
+        keys[3 * pos] = k3[0]; keys[3 * pos + 1] = k3[1]; keys[3 * pos + 2] = k3[2];
+        /* voxgraph_submap.cpp:226-241 */
+        float vd, vw;
+        if (!vgo_interp_voxel(l, p, &vd, &vw)) continue;
+        if (n < max_n) {
+          xyz[3 * n] = p[0]; xyz[3 * n + 1] = p[1]; xyz[3 * n + 2] = p[2];
+          distance[n] = vd;
+          weight[n] = vw;
+        }
+        ++n;
+        int32_t ib[3];
+        vgo_grid_index_from_point(p, l->block_size_inv, ib);
+        int seen = 0;
+        for (int k = 0; k < nb && k < max_blocks; ++k)
+          if (iso_blocks[3 * k] == ib[0] && iso_blocks[3 * k + 1] == ib[1] && iso_blocks[3 * k + 2] == ib[2]) { seen = 1; break; }
+        if (!seen) {
+          if (nb < max_blocks) { iso_blocks[3 * nb] = ib[0]; iso_blocks[3 * nb + 1] = ib[1]; iso_blocks[3 * nb + 2] = ib[2]; }
+          ++nb;
+        }
+      }
+    }
+  }
+  free(keys);
+  free(used);
+  if (n_blocks_out) *n_blocks_out = nb;
   return n;
 }
 

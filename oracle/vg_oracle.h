@@ -190,6 +190,29 @@ int vgo_graph_solve(vgo_graph* g, const vgo_solver_options* opts, vgo_solver_sum
 int vgo_find_relevant_voxels(const vgo_layer* layer, double min_voxel_weight,
                              double max_voxel_distance, float* xyz, float* distance,
                              float* weight, int max_n);
+/* VoxgraphSubmap::findIsosurfaceVertices (voxgraph_submap.cpp:203-243):
+ *   MeshIntegrator(min_weight = min_voxel_weight, use_color = false).generateMesh  (upstream voxblox
+ *   mesh_integrator.h / marching_cubes.h, restated from the published algorithm: every voxel is the
+ *   origin of a cube over its 2x2x2 forward neighbourhood - corner order (0,0,0),(1,0,0),(1,1,0),
+ *   (0,1,0),(0,0,1),(1,0,1),(1,1,1),(0,1,1) - meshed only when all 8 corners have weight >
+ *   min_weight; a vertex is interpolated on every cube edge whose end points differ in sign (sdf < 0):
+ *   v1 + sdf1 / (sdf1 - sdf2) * (v2 - v1), or the mid point when |sdf1 - sdf2| < 1e-6),
+ *   MeshLayer::getConnectedMesh(0.5 * voxel_size) (vertices are bucketed by
+ *   round(vertex / threshold) in double; the first vertex of a bucket is kept),
+ *   Interpolator::getVoxel(vertex, interpolate = true) -> trilinear (distance, weight); vertices whose
+ *   8 neighbours are not all observed are dropped.
+ * The marching-cubes triangle table only decides how often and in which order an edge vertex is
+ * emitted, not which vertices exist; the order decides which member of a bucket survives.  The
+ * reference walks blocks in hash-map order; this restatement (and the GPU path) fixes the order
+ * canonically: blocks in allocation order, voxels in linear order, cube edges 0..11.
+ * Writes at most max_n points / max_blocks isosurface block indices (cpp:237-240), returns the
+ * vertex count, *n_blocks the number of distinct isosurface blocks (first-occurrence order). */
+int vgo_find_isosurface_vertices(const vgo_layer* layer, double min_voxel_weight, float* xyz,
+                                 float* distance, float* weight, int max_n, int32_t* iso_blocks,
+                                 int max_blocks, int* n_blocks);
+/* Interpolator::getVoxel(pos, &voxel, true): trilinear distance and weight; 0 when impossible. */
+int vgo_interp_voxel(const vgo_layer* layer, const float pos[3], float* distance, float* weight);
+
 /* VoxgraphSubmap::getSubmapFrameSurfaceObb (voxgraph_submap.cpp:280-324). Returns 0 when no
  * voxel qualifies (box stays +-inf). */
 int vgo_surface_obb(const vgo_layer* layer, double min_voxel_weight, double max_voxel_distance,

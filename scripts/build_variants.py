@@ -9,13 +9,14 @@ sys.path.insert(0, ROOT)
 from voxgraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "t128_b5": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
-    "t128_b4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=4"],
-    "t128_b6": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
-    "t256_b2": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=2"],
-    "t256_b3": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=3"],
-    "t64_b10": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=10"],
-    "t128_b5_cs": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_STREAM_OCTETS=1"],
+    "t128_b5_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
+    "t128_b5_tu8": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_TILE_UNITS=8"],
+    "t128_b5_tu2": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_TILE_UNITS=2"],
+    "t128_b4_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=4"],
+    "t128_b6_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
+    "t64_b10_tu4": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=10"],
+    "t64_b12_tu4": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=12"],
+    "t256_b2_tu4": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=2"],
 }
 
 if __name__ == "__main__":

@@ -41,6 +41,11 @@ class TsdfStats(C.Structure):
                 ("voxel_updates", C.c_int64), ("blocks_allocated", C.c_int64)]
 
 
+class RegistrationFilter(C.Structure):
+    _fields_ = [("min_voxel_weight", C.c_double), ("max_voxel_distance", C.c_double),
+                ("use_esdf_distance", C.c_int)]
+
+
 class RegConfig(C.Structure):
     _fields_ = [("registration_point_type", C.c_int),
                 ("no_correspondence_cost", C.c_double),
@@ -88,7 +93,10 @@ EXPORTS = [
     "vgx_comm_init",
     "vgx_comm_destroy", "vgx_comm_p2p_export", "vgx_comm_p2p_import",
     "vgx_submap_info", "vgx_submap_draw_samples", "vgx_graph_set_registration_constraints_v",
-    "vgx_graph_get_sample_indices", "vgx_graph_set_sample_indices",
+    "vgx_graph_get_sample_indices", "vgx_graph_set_sample_indices", "vgx_comm_suspend",
+    "vgx_registration_filter_default", "vgx_submap_extract_points", "vgx_submap_finish_ex",
+    "vgx_submap_num_points", "vgx_submap_download_points", "vgx_submap_surface_obb",
+    "vgx_find_overlapping_pairs",
 ]
 
 _lib = None
@@ -145,6 +153,14 @@ def load():
     L.vgx_graph_set_registration_constraints_v.argtypes = [vp, i32, pu32, pu32, C.POINTER(RegConfig)]
     L.vgx_graph_get_sample_indices.argtypes = [vp, i32, i32, pi32, C.POINTER(i32)]
     L.vgx_graph_set_sample_indices.argtypes = [vp, i32, i32, pi32]
+    L.vgx_registration_filter_default.argtypes = [C.POINTER(RegistrationFilter)]
+    L.vgx_registration_filter_default.restype = None
+    L.vgx_submap_extract_points.argtypes = [vp, u32, C.POINTER(RegistrationFilter)]
+    L.vgx_submap_finish_ex.argtypes = [vp, u32, C.POINTER(RegistrationFilter)]
+    L.vgx_submap_num_points.argtypes = [vp, u32, i32, C.POINTER(i32)]
+    L.vgx_submap_download_points.argtypes = [vp, u32, i32, i32, pf, pf, pf, C.POINTER(i32)]
+    L.vgx_submap_surface_obb.argtypes = [vp, u32, pf, pf]
+    L.vgx_find_overlapping_pairs.argtypes = [vp, i32, pu32, pf, i32, pu32, C.POINTER(i32)]
     L.vgx_submap_info.argtypes = [vp, u32, pf, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.vgx_submap_draw_samples.argtypes = [vp, u32, i32, i32, pi32]
     L.vgx_graph_num_registration_residuals.argtypes = [vp, C.POINTER(C.c_int64),
@@ -159,6 +175,7 @@ def load():
     L.vgx_comm_unique_id.argtypes = [pu8]
     L.vgx_comm_init.argtypes = [vp, i32, i32, pu8]
     L.vgx_comm_destroy.argtypes = [vp]
+    L.vgx_comm_suspend.argtypes = [vp, i32]
     L.vgx_comm_p2p_export.argtypes = [vp, C.c_uint64, pu8]
     L.vgx_comm_p2p_import.argtypes = [vp, i32, i32, pu8]
     _lib = L

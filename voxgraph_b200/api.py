@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (RegConfig, SolverOptions, SolverSummary, TsdfConfig, TsdfStats)
+from ._lib import (RegConfig, RegistrationFilter, SolverOptions, SolverSummary, TsdfConfig, TsdfStats)
 
 K_VOXELS = 0            # VoxgraphSubmap::RegistrationPointType::kVoxels
 K_ISOSURFACE_POINTS = 1  # ...::kIsosurfacePoints
@@ -103,6 +103,54 @@ class Context:
 
     def submap_finish(self, submap_id):
         self._check(self._L.vgx_submap_finish(self._h, int(submap_id)))
+
+    def registration_filter(self, **kw):
+        f = RegistrationFilter()
+        self._L.vgx_registration_filter_default(C.byref(f))
+        for k, v in kw.items():
+            setattr(f, k, v)
+        return f
+
+    def submap_extract_points(self, submap_id, filt=None):
+        """findRelevantVoxelIndices + findIsosurfaceVertices + surface OBB on the device."""
+        self._check(self._L.vgx_submap_extract_points(self._h, int(submap_id),
+                                                      C.byref(filt) if filt is not None else None))
+
+    def submap_finish_ex(self, submap_id, filt=None):
+        self._check(self._L.vgx_submap_finish_ex(self._h, int(submap_id),
+                                                 C.byref(filt) if filt is not None else None))
+
+    def submap_num_points(self, submap_id, point_type):
+        n = C.c_int(0)
+        self._check(self._L.vgx_submap_num_points(self._h, int(submap_id), int(point_type), C.byref(n)))
+        return n.value
+
+    def submap_download_points(self, submap_id, point_type):
+        n = self.submap_num_points(submap_id, point_type)
+        xyz = np.zeros((n, 3), np.float32); d = np.zeros(n, np.float32); w = np.zeros(n, np.float32)
+        got = C.c_int(0)
+        self._check(self._L.vgx_submap_download_points(self._h, int(submap_id), int(point_type), n,
+                                                       _p(xyz, C.c_float), _p(d, C.c_float),
+                                                       _p(w, C.c_float), C.byref(got)))
+        return xyz, d, w
+
+    def submap_surface_obb(self, submap_id):
+        mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
+        rc = self._check(self._L.vgx_submap_surface_obb(self._h, int(submap_id), _p(mn, C.c_float),
+                                                        _p(mx, C.c_float)), allow=(0, 1))
+        return rc == 0, mn, mx
+
+    def find_overlapping_pairs(self, submap_ids, poses_T):
+        """updateOverlappingSubmapList: poses_T (n,7) = [qw qx qy qz tx ty tz] -> list of (id_i, id_j)."""
+        ids = np.ascontiguousarray(submap_ids, np.uint32)
+        T = _f32(poses_T).reshape(-1, 7)
+        assert T.shape[0] == len(ids)
+        cap = max(1, len(ids) * (len(ids) - 1) // 2)
+        out = np.zeros((cap, 2), np.uint32); n = C.c_int(0)
+        self._check(self._L.vgx_find_overlapping_pairs(self._h, len(ids), _p(ids, C.c_uint32),
+                                                       _p(T, C.c_float), cap, _p(out, C.c_uint32),
+                                                       C.byref(n)))
+        return [tuple(int(v) for v in out[k]) for k in range(n.value)]
 
     def submap_free(self, submap_id):
         self._check(self._L.vgx_submap_free(self._h, int(submap_id)))
@@ -274,6 +322,10 @@ class Context:
         return x, s
 
     # ---- multi-GPU
+    def comm_suspend(self, on=True):
+        """Behave as a single-rank context (full problem locally, no exchange) while on."""
+        self._check(self._L.vgx_comm_suspend(self._h, int(bool(on))))
+
     def comm_init(self, nranks, rank, unique_id):
         u = np.ascontiguousarray(unique_id, np.uint8)
         assert u.size == 128

@@ -16,6 +16,8 @@ SOURCES = [
     ("submap.cu", ["-fmad=false"]),
     ("registration.cu", ["-fmad=false"]),
     ("tsdf.cu", ["-fmad=false"]),
+    ("extract.cu", ["-fmad=false"]),
+    ("overlap.cu", ["-fmad=false"]),
     ("graph.cu", []),
     ("p2p.cu", []),
     ("nccl_dyn.cpp", []),

@@ -56,7 +56,7 @@ struct VgxGraph {
   // derived
   std::vector<int> local;  // global indices of this rank's registration constraints
   std::vector<int> block_nodes;  // E x 2 (host copy)
-  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_ctas = 0, grid_capacity = 0;
+  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_ctas = 0;
   int E = 0;               // off-diagonal blocks
   int n_free = 0;          // reduced dimension 4 * (non-constant nodes)
   int64_t residuals_local = 0, residuals_global = 0;
@@ -68,7 +68,7 @@ struct VgxGraph {
   RegPoseConst* d_poses = nullptr;
   RegTile* d_tiles = nullptr;
   int* d_tile_begin = nullptr;
-  int* d_cta_tile_begin = nullptr;
+  int* d_sched = nullptr;        // reduce kernel's ticket counter + exit counter
   double* d_partials = nullptr;
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
@@ -92,7 +92,7 @@ struct VgxGraph {
 };
 
 static void free_tables(VgxGraph* g) {
-  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_cta_tile_begin);
+  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_sched);
   cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
@@ -102,7 +102,7 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_sample_pts); cudaFree(g->d_sample_idx);
   g->d_sample_pts = nullptr; g->d_sample_idx = nullptr;
   if (g->h_state) cudaFreeHost(g->h_state);
-  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_cta_tile_begin = nullptr;
+  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_sched = nullptr;
   g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
   g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
   g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
@@ -1071,43 +1071,27 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
       VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // g->samples[] are pageable host vectors
     }
   }
-  // Cut the local residual index space into 32-point units and deal them evenly to the resident
-  // CTAs; a tile is the part of one CTA's run of units that lies inside one residual block (tiles
-  // never straddle constraints and start on a unit boundary = 128-byte aligned SoA slices for TMA).
-  g->grid_capacity = 0;
-  for (const auto& cc : cons)
-    if (cc.grid) g->grid_capacity = std::max(g->grid_capacity, cc.gd0 * cc.gd1 * cc.gd2);
-  const int n_ctas_max = std::max(vgx_reg_resident_ctas(c->device, g->grid_capacity), 1);
-  int64_t U = 0;  // total units
-  for (const auto& cc : cons) U += (cc.n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
-  g->n_ctas = (int)std::min<int64_t>(n_ctas_max, U);
-  std::vector<int> cta_tile_begin;
+  // Every constraint is cut into tiles of VGX_REG_TILE_UNITS 32-point units (128-byte aligned
+  // unit-major slices for TMA); the persistent warps of the reduce kernel draw them dynamically.
   {
-    int64_t ubase = 0;  // unit index of the current constraint's first unit
-    int cta = 0;
-    auto cta_end = [&](int k) { return (int64_t)(((__int128)U * (k + 1)) / std::max(g->n_ctas, 1)); };
-    if (g->n_ctas > 0) cta_tile_begin.push_back(0);
+    const int tile_pts = VGX_REG_TILE_UNITS * VGX_REG_UNIT;
     for (int k = 0; k < g->n_local; ++k) {
       tile_begin.push_back((int)tiles.size());
-      const int64_t uc = (cons[k].n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
-      int64_t u = 0;
-      while (u < uc) {
-        while (cta + 1 < g->n_ctas && ubase + u >= cta_end(cta)) { cta_tile_begin.push_back((int)tiles.size()); ++cta; }
-        const int64_t take = std::min<int64_t>(uc - u, cta_end(cta) - (ubase + u));
+      for (int s0 = 0; s0 < cons[k].n; s0 += tile_pts) {
         RegTile t;
-        t.constraint = k;
-        t.start = (int)(u * VGX_REG_UNIT);
-        t.count = (int)std::min<int64_t>(take * VGX_REG_UNIT, (int64_t)cons[k].n - t.start);
-        t.pad = 0;
+        t.constraint = k; t.start = s0; t.count = std::min(tile_pts, cons[k].n - s0); t.pad = 0;
         tiles.push_back(t);
-        u += take;
       }
-      ubase += uc;
     }
-    while ((int)cta_tile_begin.size() <= g->n_ctas) cta_tile_begin.push_back((int)tiles.size());
+    tile_begin.push_back((int)tiles.size());
   }
-  tile_begin.push_back((int)tiles.size());
   g->n_tiles = (int)tiles.size();
+  // persistent grid: all co-resident CTAs, but no more warps than tiles
+  {
+    const int warps_per_cta = VGX_REG_THREADS / 32;
+    const int want = (g->n_tiles + warps_per_cta - 1) / warps_per_cta;
+    g->n_ctas = std::max(0, std::min(vgx_reg_resident_ctas(c->device), want));
+  }
   g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
 
   // ---- off-diagonal block index over ALL edges (identical on every rank)
@@ -1159,7 +1143,6 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   if (e == cudaSuccess) e = upload_vec(&g->d_cons, cons, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tiles, tiles, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tile_begin, tile_begin, st);
-  if (e == cudaSuccess) e = upload_vec(&g->d_cta_tile_begin, cta_tile_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
@@ -1173,6 +1156,8 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_partials, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_tiles);
   dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
   dmalloc((void**)&g->d_counters, sizeof(int) * (size_t)g->n_local);
+  dmalloc((void**)&g->d_sched, sizeof(int) * 2);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_sched, 0, sizeof(int) * 2, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counters, 0, std::max<size_t>(sizeof(int) * (size_t)g->n_local, 4), st);
   // a constraint without points owns no tile: its sums must read as zero
   if (e == cudaSuccess) e = cudaMemsetAsync(g->d_csum, 0, std::max<size_t>(sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local, 8), st);
@@ -1208,9 +1193,8 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     {
       VgxLaunchScope s(c, 0);
-      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_ctas, g->d_cta_tile_begin,
-                            g->d_tile_begin, g->d_counters, g->d_partials, g->d_csum, g->grid_capacity,
-                            jacobian);
+      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->n_ctas, g->d_tile_begin,
+                            g->d_counters, g->d_sched, g->d_partials, g->d_csum, jacobian);
     }
   }
   // multi-rank: assemble straight into the NVLink-exported buffer when the peer path is up

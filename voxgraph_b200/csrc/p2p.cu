@@ -153,3 +153,23 @@ int vgx_p2p_gather(vgx_ctx* c, double* d_out, size_t count) {
   VGX_CUDA(c, cudaGetLastError());
   return VGX_OK;
 }
+
+extern "C" int vgx_comm_suspend(vgx_ctx* c, int on) {
+  if (!c) return VGX_ERR_INVALID;
+  if (on) {
+    if (c->saved_nranks == 0) {
+      c->saved_nranks = c->nranks;
+      c->saved_rank = c->rank;
+      c->nranks = 1;
+      c->rank = 0;
+      vgx_graph_invalidate_registration(c);
+    }
+  } else if (c->saved_nranks != 0) {
+    c->nranks = c->saved_nranks;
+    c->rank = c->saved_rank;
+    c->saved_nranks = 0;
+    c->saved_rank = 0;
+    vgx_graph_invalidate_registration(c);
+  }
+  return VGX_OK;
+}

@@ -79,181 +79,225 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Registration reduce kernel, v4.  Persistent CTAs; the local residual index space is cut into
-// 32-point units that are dealt evenly to the CTAs (a tile = a CTA's run of units inside one
-// residual block).  Inside a tile every warp runs its own software pipeline over the units
-// u = warp, warp + W, ...:
-//   * the unit's points (640 contiguous bytes of the unit-major AoSoA layout) are brought into a
-//     per-warp 4-slot shared-memory ring by ONE cp.async.bulk (TMA 1-D) completing on an
-//     mbarrier, three units ahead - the point loads never touch the LSU path of the math warps;
-//   * stage A(u+1): transform -> voxel index -> block-grid lookup (shared memory) -> the octet's
-//     two LDG.128 are ISSUED;  stage B(u): the octet issued one iteration earlier is consumed:
-//     B1 coefficients, residual, Jacobian, Gram staging + 8 DMMA.  The gather latency of unit
-//     u+1 is hidden behind the arithmetic of unit u inside the same warp.
-// The last unit is zero-padded to 32 points (weight 0 -> zero contribution), so the
-// loop carries no "active" predicate.  Warps never synchronise with each other inside a tile.
+// Registration reduce kernel, v6: warp-level dynamic scheduling.
+//
+// The residual index space of every constraint is cut into tiles of VGX_REG_TILE_UNITS 32-point
+// units (128 points).  The cost of a tile varies by 4x with the share of its points that land in
+// the reading submap (overlapping submaps share only part of their surface and consecutive
+// points are spatially coherent), so tiles are NOT pre-assigned: every warp of the persistent
+// grid draws tile tickets from a global counter and runs its own software pipeline, two tiles
+// deep, with no block-level synchronisation at all:
+//   * ticket t+2 is drawn and its points (TILE_UNITS x 640 contiguous bytes of the unit-major
+//     AoSoA layout) are requested with ONE cp.async.bulk (TMA 1-D) into the warp's 2-slot
+//     shared-memory ring, completing on an mbarrier, while tile t is processed;
+//   * per tile the constraint's descriptor + float pose block are staged in the warp's own
+//     shared-memory copy (lanes load one word each);
+//   * stage A(u+1): transform -> containing block -> block grid (global memory, L1/L2 resident,
+//     <= 16 KB per submap) -> base corner voxel -> the octet's two LDG.128 are ISSUED;
+//     stage B(u): the octet issued one unit earlier is consumed: B1 coefficients, residual,
+//     Jacobian, Gram staging + 8 DMMA.  Two register sets alternate so the in-flight octet is
+//     never copied.  A warp whose 32 points all miss the reading submap (getVoxelsAndQVector
+//     fails on its first block lookup) skips the unit after ~60 instructions;
+//   * the tile's 21 sums go to partials[tile]; the warp that finishes a constraint's last tile
+//     (atomic ticket) adds the constraint's partials in tile order -> bit-reproducible results
+//     whatever warp processed which tile.
+// The last unit of a constraint is zero-padded to 32 points (weight 0 -> zero contribution).
+#define VGX_REG_UNIT_FLOATS 160
+#define VGX_REG_TILE_BYTES (VGX_REG_TILE_UNITS * 640)
+
+struct RegPipeRegs {   // what stage A hands to stage B
+  float4 lo, hi;       // the octet (NaN when the block is missing)
+  float ox, oy, oz;
+  bool found;
+};
+
+// block grid of the reading submap in global memory (int32 slots, -1 = no block)
+__device__ __forceinline__ int vgx_grid_slot_g(const RegConstraintDev& C, int b0, int b1, int b2) {
+  const int g0 = b0 - C.gmin0, g1 = b1 - C.gmin1, g2 = b2 - C.gmin2;
+  const bool in = (unsigned)g0 < (unsigned)C.gd0 && (unsigned)g1 < (unsigned)C.gd1 &&
+                  (unsigned)g2 < (unsigned)C.gd2;
+  return in ? __ldg(C.grid + (g2 * C.gd1 + g1) * C.gd0 + g0) : -1;
+}
+
 template <bool kJacobian>
 __global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
-                  const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_begin,
-                  int* __restrict__ counters, double* __restrict__ partials,
-                  double* __restrict__ csum, int grid_capacity) {
+                  int n_tiles, const int* __restrict__ tile_begin, int* __restrict__ counters,
+                  int* __restrict__ sched /* [0] next ticket, [1] warps that have left */,
+                  double* __restrict__ partials, double* __restrict__ csum) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
-  constexpr int kRing = VGX_REG_RING;
-  __shared__ __align__(128) float s_ring[kWarps][kRing][5][32];
-  __shared__ __align__(8) unsigned long long s_bar[kWarps][kRing];
+  constexpr int kTU = VGX_REG_TILE_UNITS;
+  __shared__ __align__(128) float s_ring[kWarps][2][kTU * VGX_REG_UNIT_FLOATS];
+  __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
   __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
   __shared__ double s_gram[kWarps][64];
-  __shared__ RegConstraintDev s_C;
-  __shared__ RegPoseConst s_P;
-  __shared__ int s_last;
-  extern __shared__ int32_t s_grid[];
+  __shared__ __align__(16) RegConstraintDev s_Cw[kWarps];
+  __shared__ __align__(16) RegPoseConst s_Pw[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
+  const RegConstraintDev& C = s_Cw[warp];
   if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kRing; ++k) mbar_init(smem_u32(&s_bar[warp][k]), 1);
+    mbar_init(smem_u32(&s_bar[warp][0]), 1);
+    mbar_init(smem_u32(&s_bar[warp][1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  const uint32_t ring0 = smem_u32(&s_ring[warp][0][0][0]);
+  __syncwarp();
+  const uint32_t ring0 = smem_u32(&s_ring[warp][0][0]);
   const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
-  const float* ringf = &s_ring[warp][0][0][0];
+  const float* ringf = &s_ring[warp][0][0] + lane;
   double* stage_w = &s_stage[warp][0][lane];
   const double* stage_r = &s_stage[warp][grp < 6 ? grp : 0][tig];
-  uint32_t it = 0;   // units consumed by this warp so far: ring slot = it % kRing, parity = (it / kRing) & 1
-  int grid_of = -1;  // constraint whose block grid is currently staged
 
-  for (int tile = cta_tile_begin[blockIdx.x]; tile < cta_tile_begin[blockIdx.x + 1]; ++tile) {
-    const RegTile T = tiles[tile];
-    __syncthreads();  // previous tile: every warp is out of its loop (s_C / s_P / s_grid readers)
+  auto draw = [&]() -> int {  // next tile ticket, warp-uniform
+    int t = 0;
+    if (lane == 0) t = atomicAdd(sched, 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  // request tile t's points into ring slot `slot` (lane 0); returns the tile record to all lanes
+  auto request = [&](int t, uint32_t slot) -> RegTile {
+    RegTile T;
+    T.constraint = -1; T.start = 0; T.count = 0; T.pad = 0;
+    if (t < n_tiles) {
+      const int4 raw = __ldg(reinterpret_cast<const int4*>(tiles + t));
+      T.constraint = raw.x; T.start = raw.y; T.count = raw.z;
+      if (lane == 0) {
+        const float* src = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(
+                               &constraints[T.constraint].pts))) +
+                           (size_t)(T.start >> 5) * VGX_REG_UNIT_FLOATS;
+        const uint32_t bytes = 640u * (uint32_t)((T.count + 31) >> 5);
+        mbar_expect_tx(bar0 + 8u * slot, bytes);
+        tma_load_1d(ring0 + (uint32_t)VGX_REG_TILE_BYTES * slot, src, bytes, bar0 + 8u * slot);
+      }
+    }
+    return T;
+  };
+
+  uint32_t seq = 0;  // tiles consumed by this warp: ring slot = seq & 1, barrier parity = (seq >> 1) & 1
+  int t_cur = draw();
+  RegTile T_cur = request(t_cur, 0);
+  int t_nxt = draw();
+  RegTile T_nxt = request(t_nxt, 1);
+
+  while (t_cur < n_tiles) {
+    const uint32_t slot = seq & 1u;
+    // ---- stage the constraint descriptor + pose block in the warp's shared-memory copy
     {
       constexpr int kWc = (int)(sizeof(RegConstraintDev) / 4), kWp = (int)(sizeof(RegPoseConst) / 4);
-      for (int k = threadIdx.x; k < kWc + kWp; k += VGX_REG_THREADS) {
-        if (k < kWc)
-          reinterpret_cast<uint32_t*>(&s_C)[k] =
-              __ldg(reinterpret_cast<const uint32_t*>(constraints + T.constraint) + k);
-        else
-          reinterpret_cast<uint32_t*>(&s_P)[k - kWc] =
-              __ldg(reinterpret_cast<const uint32_t*>(poses + T.constraint) + (k - kWc));
-      }
+      const uint32_t* gc = reinterpret_cast<const uint32_t*>(constraints + T_cur.constraint);
+      const uint32_t* gp = reinterpret_cast<const uint32_t*>(poses + T_cur.constraint);
+      uint32_t* sc = reinterpret_cast<uint32_t*>(&s_Cw[warp]);
+      uint32_t* sp = reinterpret_cast<uint32_t*>(&s_Pw[warp]);
+      for (int k = lane; k < kWc; k += 32) sc[k] = __ldg(gc + k);
+      if (lane < kWp) sp[lane] = __ldg(gp + lane);
+      __syncwarp();
     }
-    __syncthreads();
-    const int cells = s_C.gd0 * s_C.gd1 * s_C.gd2;
-    const bool use_grid = s_C.grid != nullptr && cells <= grid_capacity;
-    if (use_grid && grid_of != T.constraint) {
-      const int32_t* gsrc = s_C.grid;
-      for (int k = threadIdx.x; k < cells; k += VGX_REG_THREADS) s_grid[k] = __ldg(gsrc + k);
-      grid_of = T.constraint;
-      __syncthreads();
-    }
-    const RegPoseConst P = s_P;
+    const RegPoseConst P = s_Pw[warp];
+    const int n_units = (T_cur.count + 31) >> 5;
+    const bool use_grid = C.grid != nullptr;
+    const size_t vox_shift = 3 * C.vps_shift;
+    const float4* view = reinterpret_cast<const float4*>(C.view);
+    const bool gram_always = C.no_corr != 0.0;  // r = w * no_correspondence_cost without a match
+    const float* tile_ring = ringf + slot * (kTU * VGX_REG_UNIT_FLOATS);
     double d0 = 0.0, d1 = 0.0;
-    const int n_units = (T.count + 31) >> 5;
-    const int my_units = warp < n_units ? (n_units - warp + kWarps - 1) / kWarps : 0;
-    const size_t vox_shift = 3 * s_C.vps_shift;
-    const float4* view = reinterpret_cast<const float4*>(s_C.view);
+    mbar_wait(bar0 + 8u * slot, (seq >> 1) & 1u);  // this tile's points have landed
 
-    // producer (lane 0): bring unit j of this warp into ring slot (it + j - j_consumed)
-    auto issue = [&](int j, uint32_t seq) {
-      if (lane == 0) {
-        const uint32_t slot = seq % kRing;
-        const uint32_t bar = bar0 + 8u * slot, dst = ring0 + 640u * slot;
-        const size_t unit = (size_t)(T.start >> 5) + (size_t)(warp + j * kWarps);
-        mbar_expect_tx(bar, 640u);
-        tma_load_1d(dst, s_C.pts + unit * VGX_PT_UNIT_FLOATS, 640u, bar);
-      }
-    };
     // stage A: everything up to the ISSUE of the octet loads
-    float4 lo, hi;
-    float ox, oy, oz;
-    bool found;
-    auto stage_a = [&](uint32_t seq, float4& alo, float4& ahi, float& aox, float& aoy, float& aoz,
-                       bool& afound) {
-      const uint32_t slot = seq % kRing;
-      mbar_wait(bar0 + 8u * slot, (seq / kRing) & 1u);
-      const float* sp = ringf + 160 * slot + lane;
+    auto stage_a = [&](int u, RegPipeRegs& R) {
+      const float* sp = tile_ring + u * VGX_REG_UNIT_FLOATS;
       float p0, p1, p2;
       vgx_reg_transform(P, sp[0], sp[32], sp[64], p0, p1, p2);
+      const float qnan = __int_as_float(0x7fc00000);
+      R.lo = make_float4(qnan, qnan, qnan, qnan);
+      R.hi = R.lo;
+      R.found = false;
+      R.ox = R.oy = R.oz = 0.f;
+      int b0, b1, b2;
+      vgx_block_index(C, p0, p1, p2, b0, b1, b2);
       RegLocate L;
       int slot_b;
       if (use_grid) {
-        vgx_locate<true>(s_C, p0, p1, p2, L, s_grid);
-        slot_b = L.slot;
+        // getVoxelsAndQVector fails right away when the block that contains pos does not exist
+        const bool hit = vgx_grid_slot_g(C, b0, b1, b2) >= 0;
+        if (!__any_sync(0xffffffffu, hit)) return;
+        vgx_locate_in_block<false>(C, p0, p1, p2, b0, b1, b2, L, nullptr, true);
+        slot_b = hit ? vgx_grid_slot_g(C, L.b0, L.b1, L.b2) : -1;
       } else {
-        vgx_locate<false>(s_C, p0, p1, p2, L);
-        slot_b = vgx_resolve(s_C, L);
+        vgx_locate_in_block<false>(C, p0, p1, p2, b0, b1, b2, L);
+        slot_b = vgx_resolve(C, L);
       }
-      afound = slot_b >= 0;
-      aox = L.ox; aoy = L.oy; aoz = L.oz;
-      const float qnan = __int_as_float(0x7fc00000);
-      alo = make_float4(qnan, qnan, qnan, qnan);
-      ahi = alo;
-      if (afound) {
+      R.found = slot_b >= 0;
+      R.ox = L.ox; R.oy = L.oy; R.oz = L.oz;
+      if (R.found) {
         const float4* o = view + 2 * (((size_t)slot_b << vox_shift) + (size_t)L.lin);
 #if VGX_REG_STREAM_OCTETS
-        alo = __ldcs(o); ahi = __ldcs(o + 1);
+        R.lo = __ldcs(o); R.hi = __ldcs(o + 1);
 #else
-        alo = __ldg(o); ahi = __ldg(o + 1);
+        R.lo = __ldg(o); R.hi = __ldg(o + 1);
 #endif
       }
     };
-
-    if (my_units > 0) {
+    // stage B: consume the octet issued one unit ago
+    auto stage_b = [&](int u, const RegPipeRegs& R) {
+      const float* sp = tile_ring + u * VGX_REG_UNIT_FLOATS;
+      const float d[8] = {R.lo.x, R.lo.y, R.lo.z, R.lo.w, R.hi.x, R.hi.y, R.hi.z, R.hi.w};
+      bool ok = false;
+      if (__any_sync(0xffffffffu, R.found)) ok = R.found && vgx_octet_ok(d);
+      if (gram_always || __any_sync(0xffffffffu, ok)) {
+        const float xi = sp[0], yi = sp[32], dist = sp[96], w = sp[128];
+        const RegPointResult Q = vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, R.ox, R.oy, R.oz);
+        if (kJacobian) {
+          stage_w[0 * VGX_STAGE_STRIDE] = (double)Q.jr[0];
+          stage_w[1 * VGX_STAGE_STRIDE] = (double)Q.jr[1];
+          stage_w[2 * VGX_STAGE_STRIDE] = (double)Q.jr[2];
+          stage_w[3 * VGX_STAGE_STRIDE] = (double)Q.jr[3];
+          stage_w[4 * VGX_STAGE_STRIDE] = (double)Q.je3;
+          stage_w[5 * VGX_STAGE_STRIDE] = Q.r;
+          __syncwarp();
 #pragma unroll
-      for (int j = 0; j < kRing - 1; ++j)
-        if (j < my_units) issue(j, it + j);
-      stage_a(it, lo, hi, ox, oy, oz, found);
-    }
-    for (int j = 0; j < my_units; ++j, ++it) {
-      // slot of unit j-1 is free: every lane finished its stage B (the __syncwarp after the DMMAs)
-      if (j + kRing - 1 < my_units) issue(j + kRing - 1, it + kRing - 1);
-      float4 nlo, nhi;
-      float nox = 0.f, noy = 0.f, noz = 0.f;
-      bool nfound = false;
-      if (j + 1 < my_units) stage_a(it + 1, nlo, nhi, nox, noy, noz, nfound);
-      // ---- stage B: consume the octet issued one iteration ago
-      const float* sp = ringf + 160 * (it % kRing) + lane;
-      const float xi = sp[0], yi = sp[32], dist = sp[96], w = sp[128];
-      const float d[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-      const bool ok = found && vgx_octet_ok(d);
-      const RegPointResult R = vgx_reg_math<kJacobian>(s_C, P, xi, yi, dist, w, ok, d, ox, oy, oz);
-      if (kJacobian) {
-        stage_w[0 * VGX_STAGE_STRIDE] = (double)R.jr[0];
-        stage_w[1 * VGX_STAGE_STRIDE] = (double)R.jr[1];
-        stage_w[2 * VGX_STAGE_STRIDE] = (double)R.jr[2];
-        stage_w[3 * VGX_STAGE_STRIDE] = (double)R.jr[3];
-        stage_w[4 * VGX_STAGE_STRIDE] = (double)R.je3;
-        stage_w[5 * VGX_STAGE_STRIDE] = R.r;
-        __syncwarp();
-#pragma unroll
-        for (int t4 = 0; t4 < 8; ++t4) {
-          const double a = (grp < 6) ? stage_r[4 * t4] : 0.0;
-          dmma_8x8x4(d0, d1, a, a);
+          for (int t4 = 0; t4 < 8; ++t4) {
+            const double a = (grp < 6) ? stage_r[4 * t4] : 0.0;
+            dmma_8x8x4(d0, d1, a, a);
+          }
+          __syncwarp();
+        } else {
+          d0 = fma(Q.r, Q.r, d0);
         }
-        __syncwarp();
-      } else {
-        d0 = fma(R.r, R.r, d0);
-        __syncwarp();
       }
-      lo = nlo; hi = nhi; ox = nox; oy = noy; oz = noz; found = nfound;
+    };
+
+    {
+      RegPipeRegs Ra, Rb;
+      stage_a(0, Ra);
+      int u = 0;
+      for (; u + 2 <= n_units; u += 2) {
+        stage_a(u + 1, Rb);
+        stage_b(u, Ra);
+        if (u + 2 < n_units) stage_a(u + 2, Ra);
+        stage_b(u + 1, Rb);
+      }
+      if (u < n_units) stage_b(u, Ra);
     }
-    // ---- tile epilogue: warp Gram fragments -> 21 sums -> partials[tile]
+    __syncwarp();  // every lane is done with the ring slot and the constants
+    // ---- the slot is free: draw the ticket after next and request its points
+    const int t_new = draw();
+    const RegTile T_new = request(t_new, slot);
+
+    // ---- tile epilogue: warp Gram fragment -> 21 sums -> partials[tile]
     if (kJacobian) {
       s_gram[warp][grp * 8 + 2 * tig] = d0;
       s_gram[warp][grp * 8 + 2 * tig + 1] = d1;
     } else {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, off);
-      if (lane == 0) s_gram[warp][0] = d0;
     }
-    __syncthreads();
-    const double factor = s_C.factor;
-    if (threadIdx.x < VGX_REG_NSUM) {
+    __syncwarp();
+    const int cidx = T_cur.constraint;
+    const double factor = C.factor;
+    if (lane < VGX_REG_NSUM) {
       // entry e of the 21 sums -> (row, col) of the Gram matrix
       int row = 5, col = 5;
-      const int e = threadIdx.x;
+      const int e = lane;
       if (e < 15) {
         int p = 0, rem = e;
         while (rem >= 5 - p) { rem -= 5 - p; ++p; }
@@ -261,40 +305,40 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       } else if (e < 20) {
         row = e - 15; col = 5;
       }
-      double s = 0;
-      if (kJacobian) {
-#pragma unroll
-        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][row * 8 + col];
-      } else if (e == 20) {
-#pragma unroll
-        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
-      }
-      partials[(size_t)tile * VGX_REG_NSTRIDE + e] = s;
-    }
-    // The last tile of a constraint to finish sums the constraint's partials in tile order
-    // (bit-reproducible) and applies factor^2 (cpp:274-291).
-    const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
-    if (t1 - t0 == 1) {
-      if (threadIdx.x < VGX_REG_NSUM)  // single tile: no ticket needed (same thread wrote the partial)
-        csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] =
-            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (factor * factor);
-    } else {
+      double sv = 0;
+      if (kJacobian) sv = s_gram[warp][row * 8 + col];
+      else if (e == 20) sv = d0;
+      partials[(size_t)t_cur * VGX_REG_NSTRIDE + e] = sv;
       __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const int done = atomicAdd(counters + T.constraint, 1);
-        s_last = (done == t1 - t0 - 1);
+    }
+    __syncwarp();
+    // the warp that completes the constraint adds its partials in tile order (cpp:274-291: factor^2)
+    const int t0 = tile_begin[cidx], t1 = tile_begin[cidx + 1];
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(counters + cidx, 1) == t1 - t0 - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      if (lane < VGX_REG_NSUM) {
+        double sv = 0;
+        for (int t = t0; t < t1; ++t) sv += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + lane);
+        csum[(size_t)cidx * VGX_REG_NSTRIDE + lane] = sv * (factor * factor);
       }
-      __syncthreads();
-      if (s_last) {
-        __threadfence();
-        if (threadIdx.x < VGX_REG_NSUM) {
-          double s = 0;
-          for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
-          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (factor * factor);
-        }
-        if (threadIdx.x == 0) counters[T.constraint] = 0;
-      }
+      if (lane == 0) counters[cidx] = 0;
+    }
+    __syncwarp();
+    t_cur = t_nxt; T_cur = T_nxt;
+    t_nxt = t_new; T_nxt = T_new;
+    ++seq;
+  }
+  // ---- the last warp to leave re-arms the scheduler for the next launch
+  if (lane == 0) {
+    const int total = (int)(gridDim.x * kWarps);
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == total - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
     }
   }
 }
@@ -317,27 +361,22 @@ void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, co
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
-                           const int* tile_begin, int* counters, double* partials, double* csum,
-                           int grid_capacity, bool jacobian) {
-  if (n_ctas <= 0) return;
-  const size_t smem = sizeof(int32_t) * (size_t)grid_capacity;
+                           const RegTile* tiles, int n_tiles, int n_ctas, const int* tile_begin,
+                           int* counters, int* sched, double* partials, double* csum, bool jacobian) {
+  if (n_ctas <= 0 || n_tiles <= 0) return;
   if (jacobian)
-    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
-                                                                  tile_begin, counters, partials, csum,
-                                                                  grid_capacity);
+    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, n_tiles, tile_begin,
+                                                               counters, sched, partials, csum);
   else
-    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
-                                                                   tile_begin, counters, partials, csum,
-                                                                   grid_capacity);
+    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, n_tiles, tile_begin,
+                                                                counters, sched, partials, csum);
 }
 
-int vgx_reg_resident_ctas(int device, int grid_capacity) {
+int vgx_reg_resident_ctas(int device) {
   int sms = 148, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const size_t smem = sizeof(int32_t) * (size_t)grid_capacity;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_reduce_kernel<true>, VGX_REG_THREADS,
-                                                    smem) != cudaSuccess || per_sm <= 0)
+                                                    0) != cudaSuccess || per_sm <= 0)
     per_sm = VGX_REG_MIN_BLOCKS;
   static const char* env = getenv("VGX_REG_CTAS_PER_SM");  // tuning override
   if (env && atoi(env) > 0) per_sm = atoi(env);

@@ -144,15 +144,33 @@ struct RegLocate {
   uint64_t key;
   int4 e;             // probed entry
   int slot;           // kGrid: resolved directly from the shared-memory block grid
+  int b0, b1, b2;     // block of the base corner voxel
 };
 
+// step (1) of getVoxelsAndQVector: index of the block that contains pos
+__device__ __forceinline__ void vgx_block_index(const RegConstraintDev& C, float p0, float p1, float p2,
+                                                int& b0, int& b1, int& b2) {
+  b0 = vgx_floor_idx(p0 * C.block_size_inv + VGX_COORD_EPS);
+  b1 = vgx_floor_idx(p1 * C.block_size_inv + VGX_COORD_EPS);
+  b2 = vgx_floor_idx(p2 * C.block_size_inv + VGX_COORD_EPS);
+}
+
+// shared-memory block grid, 16-bit slots (0xFFFF = no block) -> brick slot or -1
+__device__ __forceinline__ int vgx_grid_slot(const RegConstraintDev& C, const uint16_t* __restrict__ s_grid,
+                                             int b0, int b1, int b2) {
+  const int g0 = b0 - C.gmin0, g1 = b1 - C.gmin1, g2 = b2 - C.gmin2;
+  const bool in = (unsigned)g0 < (unsigned)C.gd0 && (unsigned)g1 < (unsigned)C.gd1 &&
+                  (unsigned)g2 < (unsigned)C.gd2;
+  const int gs = in ? (int)s_grid[(g2 * C.gd1 + g1) * C.gd0 + g0] : 0xFFFF;
+  return gs == 0xFFFF ? -1 : gs;
+}
+
 template <bool kGrid>
-__device__ __forceinline__ void vgx_locate(const RegConstraintDev& C, float p0, float p1, float p2,
-                                           RegLocate& L, const int32_t* __restrict__ s_grid = nullptr) {
+__device__ __forceinline__ void vgx_locate_in_block(const RegConstraintDev& C, float p0, float p1,
+                                                    float p2, int b0, int b1, int b2, RegLocate& L,
+                                                    const uint16_t* __restrict__ s_grid = nullptr,
+                                                    bool no_lookup = false) {
   const int vps = C.vps;
-  int b0 = vgx_floor_idx(p0 * C.block_size_inv + VGX_COORD_EPS);
-  int b1 = vgx_floor_idx(p1 * C.block_size_inv + VGX_COORD_EPS);
-  int b2 = vgx_floor_idx(p2 * C.block_size_inv + VGX_COORD_EPS);
   const float or0 = (float)b0 * C.block_size, or1 = (float)b1 * C.block_size,
               or2 = (float)b2 * C.block_size;
   int v0 = vgx_floor_idx((p0 - or0) * C.voxel_size_inv + VGX_COORD_EPS);
@@ -170,12 +188,10 @@ __device__ __forceinline__ void vgx_locate(const RegConstraintDev& C, float p0, 
   if (p2 - (or2 + ((float)v2 + 0.5f) * C.voxel_size) < 0) {
     if (--v2 < 0) { --b2; v2 += vps; }
   }
+  L.b0 = b0; L.b1 = b1; L.b2 = b2;
   if (kGrid) {
-    const int g0 = b0 - C.gmin0, g1 = b1 - C.gmin1, g2 = b2 - C.gmin2;
-    const bool in = (unsigned)g0 < (unsigned)C.gd0 && (unsigned)g1 < (unsigned)C.gd1 &&
-                    (unsigned)g2 < (unsigned)C.gd2;
-    L.slot = in ? s_grid[(g2 * C.gd1 + g1) * C.gd0 + g0] : -1;
-  } else {
+    L.slot = vgx_grid_slot(C, s_grid, b0, b1, b2);
+  } else if (!no_lookup) {
     L.key = vgx_pack_key(b0, b1, b2);
     L.h = vgx_hash_index(b0, b1, b2, C.hash.mask);
     L.e = __ldg(reinterpret_cast<const int4*>(C.hash.entries + L.h));
@@ -186,6 +202,14 @@ __device__ __forceinline__ void vgx_locate(const RegConstraintDev& C, float p0, 
   L.oz = (p2 - ((float)b2 * C.block_size + ((float)v2 + 0.5f) * C.voxel_size)) * C.voxel_size_inv;
   const int sh = C.vps_shift;
   L.lin = v0 + (v1 << sh) + (v2 << (2 * sh));
+}
+
+template <bool kGrid>
+__device__ __forceinline__ void vgx_locate(const RegConstraintDev& C, float p0, float p1, float p2,
+                                           RegLocate& L, const uint16_t* __restrict__ s_grid = nullptr) {
+  int b0, b1, b2;
+  vgx_block_index(C, p0, p1, p2, b0, b1, b2);
+  vgx_locate_in_block<kGrid>(C, p0, p1, p2, b0, b1, b2, L, s_grid);
 }
 
 __device__ __forceinline__ int vgx_resolve(const RegConstraintDev& C, RegLocate& L) {

@@ -12,8 +12,8 @@ struct RegPoseConst;
 #ifndef VGX_REG_MIN_BLOCKS
 #define VGX_REG_MIN_BLOCKS 5       // resident CTAs per SM the register budget is sized for
 #endif
-#ifndef VGX_REG_RING
-#define VGX_REG_RING 4             // point-slice ring slots per warp (units in flight = RING - 1)
+#ifndef VGX_REG_TILE_UNITS
+#define VGX_REG_TILE_UNITS 4       // units (x 32 points, x 640 B) per tile = per ticket = per TMA bulk copy
 #endif
 #define VGX_REG_UNIT 32            // points per unit = one warp iteration; tiles are cut on unit boundaries
 #ifndef VGX_REG_STREAM_OCTETS
@@ -31,14 +31,13 @@ struct RegTile {
 
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n);
-// Persistent CTAs walk their tiles -> partial sums -> (last tile of each constraint)
-// per-constraint sums csum[c][21].
+// Persistent warps draw tile tickets -> partial sums -> (last tile of each constraint)
+// per-constraint sums csum[c][21].  sched: 2 ints, zero before the first launch (the kernel re-arms it).
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
-                           const int* tile_begin, int* counters, double* partials, double* csum,
-                           int grid_capacity, bool jacobian);
-// persistent grid size: SMs x CTAs that are co-resident with `grid_capacity` cells of dynamic smem
-int vgx_reg_resident_ctas(int device, int grid_capacity);
+                           const RegTile* tiles, int n_tiles, int n_ctas, const int* tile_begin,
+                           int* counters, int* sched, double* partials, double* csum, bool jacobian);
+// persistent grid size: SMs x co-resident CTAs
+int vgx_reg_resident_ctas(int device);
 // Fills the descriptor of one (reference -> reading) residual block.  Deterministic mode: pts / n /
 // factor describe all registration points.  Sampling mode (*sampled = true): n = int(ratio * K),
 // factor = 1 (all weights forced to 1) and pts is left null for the caller, who draws the

@@ -86,6 +86,7 @@ static void free_submap(VgxSubmap* s) {
   cudaFree(s->d_view);
   cudaFree(s->d_counters);
   cudaFree(s->d_grid);
+  cudaFree(s->d_iso_idx);
   free_points(s->points[0]);
   free_points(s->points[1]);
   delete s;
@@ -243,7 +244,8 @@ int vgx_submap_build_grid(vgx_ctx* c, VgxSubmap* s) {
       hi[a] = std::max(hi[a], idx[3 * i + a]);
     }
   const long long cells = (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
-  if (cells > VGX_GRID_MAX_CELLS) return VGX_OK;  // sparse / huge: registration uses the hash
+  // sparse / huge: registration uses the hash (the kernel stages the grid as 16-bit slots)
+  if (cells > VGX_GRID_MAX_CELLS || n >= 0xFFFF) return VGX_OK;
   std::vector<int32_t> grid((size_t)cells, -1);
   const int dx = hi[0] - lo[0] + 1, dy = hi[1] - lo[1] + 1;
   for (int i = 0; i < n; ++i)

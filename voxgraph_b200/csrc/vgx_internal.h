@@ -110,6 +110,13 @@ struct VgxSubmap {
   int grid_min[3] = {0, 0, 0};
   int grid_dim[3] = {0, 0, 0};
   VgxPoints points[2];
+  // vgx_submap_extract_points: surface OBB (cpp:280-324) and isosurface block slots (cpp:237-240)
+  bool surface_obb_valid = false;
+  float surface_obb_min[3] = {0, 0, 0}, surface_obb_max[3] = {0, 0, 0};
+  std::vector<int> iso_blocks;
+  bool points_extracted = false;
+  int32_t* d_iso_idx = nullptr;   // block indices of the isosurface blocks (n_iso x 3)
+  int n_iso = 0;
 };
 
 // ------------------------------------------------------------------ pose graph
@@ -148,6 +155,7 @@ struct vgx_ctx {
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  int saved_nranks = 0, saved_rank = 0;   // vgx_comm_suspend
   // NVLink peer exchange (CUDA IPC): region = [flags 256 B | buf0 | buf1]
   void* p2p_base = nullptr;        // own region
   void* p2p_peer[8] = {nullptr};   // mapped regions of all ranks (own entry = p2p_base)
@@ -188,6 +196,9 @@ struct VgxLaunchScope {
 };
 
 int vgx_submap_build_grid(vgx_ctx* ctx, VgxSubmap* s);
+// hand-written exclusive scan (extract.cu): out[0..n], out[n] = total; d_tmp: vgx_scan_tmp_count(n) words
+int vgx_exclusive_scan_u32(vgx_ctx* c, const unsigned* d_in, unsigned* d_out, size_t n, unsigned* d_tmp);
+size_t vgx_scan_tmp_count(size_t n);
 // WeightedSampler::getRandomItem x count on the sampler's own generator (host)
 void vgx_points_draw(VgxPoints& p, int count, int32_t* idx);
 void vgx_graph_free(vgx_ctx* ctx);

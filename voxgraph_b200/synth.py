@@ -274,9 +274,14 @@ def compose_pose(p, t_rel, yaw_rel):
     return out
 
 
+def _make_submap_job(job):
+    world, i, pose, voxel_size, vps, radius, n_points, trunc = job
+    return make_submap(world, i, pose, voxel_size, vps, radius, n_points=n_points, trunc=trunc)
+
+
 def make_scene(seed=2, n_submaps=50, n_points=10000, voxel_size=0.2, vps=16, radius=12.0,
                size_xy=(120.0, 80.0), max_pairs=None, pose_noise=(0.2, 0.05, 0.02),
-               n_clutter=400, n_walls=24, trunc=None, trajectory=None, drift=None):
+               n_clutter=400, n_walls=24, trunc=None, trajectory=None, drift=None, workers=1):
     """Config-2 style scene: N submaps along a figure-8 through a cluttered hall.
 
     drift=(sigma_xy, sigma_z, sigma_yaw) per odometry step: the initial poses are the integrated
@@ -291,8 +296,15 @@ def make_scene(seed=2, n_submaps=50, n_points=10000, voxel_size=0.2, vps=16, rad
     poses_gt = np.stack([x, y, np.full(n_submaps, 1.0), yaw], -1)
     yaw_w = poses_gt[:, 3]
     poses_gt[:, 3] = yaw_w - 2 * np.pi * np.floor((yaw_w + np.pi) / (2 * np.pi))
-    submaps = [make_submap(world, i, poses_gt[i], voxel_size, vps, radius, n_points=n_points,
-                           trunc=trunc) for i in range(n_submaps)]
+    jobs = [(world, i, poses_gt[i], voxel_size, vps, radius, n_points, trunc) for i in range(n_submaps)]
+    if workers > 1 and n_submaps > 1:
+        # host-side numpy sampling of the analytic world; one process per submap (fork: call this
+        # before the process initialises CUDA)
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, n_submaps)) as pool:
+            submaps = pool.map(_make_submap_job, jobs, chunksize=1)
+    else:
+        submaps = [_make_submap_job(j) for j in jobs]
     odometry = []
     if drift is None:
         noise = np.concatenate([rng.normal(0, pose_noise[0], (n_submaps, 2)),
