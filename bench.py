@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config4"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config4", "stream"],
                     help="auto: config2 at N = 1 (+ a config4 leg), config4 (strong scaling) at N > 1")
     ap.add_argument("--submaps", type=int, default=None)
     ap.add_argument("--pairs", type=int, default=None)
@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--voxel-size", type=float, default=None)
     ap.add_argument("--no-extras", action="store_true", help="skip solve / TSDF / CPU baseline / config4 legs")
     ap.add_argument("--no-config4", action="store_true", help="N = 1: skip the config4 leg")
+    ap.add_argument("--no-stream", action="store_true", help="N = 1: skip the streaming (configs[2]) leg")
+    ap.add_argument("--stream-scans", type=int, default=40)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     return ap.parse_args()
 
@@ -117,6 +119,149 @@ def build_scene(w, rank=0, wait_s=1500.0):
     except Exception:
         pass
     return sc
+
+
+def _scan_job(job):
+    from voxgraph_b200 import synth
+    world, pose, kind, seed = job
+    if kind == "lidar":
+        return synth.lidar_scan(world, pose, n_beams=64, n_azimuth=1024, seed=seed, max_range=16.0)
+    return synth.depth_scan(world, pose, seed=seed)
+
+
+def build_stream(kind, n_scans, rank=0, wait_s=900.0):
+    """Synthetic sensor stream (SURVEY §8d cfg 3 / cfg 5): the sensor moves at 2 m/s through the hall;
+    kind = "lidar": 64 x 1024 beams @ 10 Hz; "rgbd": 640 x 480 depth @ 30 Hz (<= 5 m).  Odometry =
+    ground truth + integrated drift.  Host-side numpy ray casting, forked workers, cached in /tmp."""
+    from voxgraph_b200 import synth
+    path = "/tmp/vgx_stream_v2_%s_%d.pkl" % (kind, n_scans)
+
+    def load():
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            return None
+    st = load() if os.path.exists(path) else None
+    if st is not None:
+        return st
+    if rank != 0:
+        t0 = time.time()
+        while time.time() - t0 < wait_s:
+            st = load() if os.path.exists(path) else None
+            if st is not None:
+                return st
+            time.sleep(1.0)
+        raise RuntimeError("stream cache %s did not appear" % path)
+    world = synth.make_world(3, size_xy=(120.0, 80.0), n_clutter=400, n_walls=24)
+    hz = 10.0 if kind == "lidar" else 30.0
+    dt = 1.0 / hz
+    rng = np.random.default_rng(3)
+    # a gentle arc through the hall at 2 m/s
+    s_arc = np.arange(n_scans) * dt * 2.0
+    x = 20.0 + s_arc * np.cos(0.15) ; y = 20.0 + s_arc * np.sin(0.15) + 3.0 * np.sin(s_arc / 9.0)
+    yaw = np.arctan2(np.gradient(y), np.gradient(x)) if n_scans > 1 else np.zeros(1)
+    gt = np.stack([x, y, np.full(n_scans, 1.2), yaw], -1)
+    odo = gt.copy()
+    drift = np.cumsum(rng.normal(0, 1.0, (n_scans, 4)) * np.array([0.004, 0.004, 0.0005, 0.0004]), 0)
+    odo += drift
+    import multiprocessing as mp
+    workers = max(1, min(64, (os.cpu_count() or 2) - 2))
+    jobs = [(world, gt[k], kind, 100 + k) for k in range(n_scans)]
+    with mp.get_context("fork").Pool(min(workers, n_scans)) as pool:
+        scans = pool.map(_scan_job, jobs, chunksize=1)
+    st = {"kind": kind, "hz": hz, "gt": gt, "odom": odo, "scans": [np.ascontiguousarray(p, np.float32) for p in scans]}
+    try:
+        tmp = path + ".%d" % os.getpid()
+        with open(tmp, "wb") as f:
+            pickle.dump(st, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return st
+
+
+def stream_leg(ctx, api, st, voxel_size, scans_per_submap, peak, cpu_scans=3):
+    """BASELINE configs[2]-shaped run: scans -> TSDF integration (Fast, as voxgraph) -> every
+    `scans_per_submap` scans: finish the submap on the device (view + registration points + OBB),
+    overlap detection, registration constraints, LM solve - the reference's
+    VoxgraphMapper::pointcloudCallback order (voxgraph_mapper.cpp:202-265, 457-524)."""
+    from oracle import oracle as o
+    from voxgraph_b200 import mapper as vm
+    hz = st["hz"]
+    trunc = 3.0 * voxel_size
+    cfg = vm.MapperConfig(voxel_size=voxel_size, submap_creation_interval=scans_per_submap / hz,
+                          capacity_blocks=16384 if voxel_size >= 0.1 else 32768,
+                          tsdf=dict(default_truncation_distance=trunc,
+                                    max_ray_length_m=16.0 if st["kind"] == "lidar" else 5.0))
+    # warm-up: module load, scratch growth
+    ctx.submap_create(9 * 10 ** 5, voxel_size, 16, cfg.capacity_blocks)
+    wcfg = ctx.tsdf_config(mode=1, default_truncation_distance=trunc)
+    for k in range(2):
+        ctx.tsdf_integrate(9 * 10 ** 5, np.array([1, 0, 0, 0, 0, 0, 0], np.float32), st["scans"][k], wcfg)
+    ctx.submap_free(9 * 10 ** 5)
+    m = vm.VoxgraphMapper(ctx, cfg, first_submap_id=2 * 10 ** 5)
+    n = len(st["scans"])
+    ctx.profile_reset(); ctx.profile_enable(True)
+    per_scan = []
+    t_all = time.time()
+    for k in range(n):
+        t0 = time.time()
+        m.pointcloudCallback(k / hz, st["odom"][k], st["scans"][k])
+        per_scan.append(time.time() - t0)
+    ctx.synchronize()
+    wall = time.time() - t_all
+    k_ms, k_n = ctx.profile_get(2)
+    ctx.profile_enable(False)
+    upd = sum(int(s.voxel_updates) for s in m.scan_stats)
+    rays = sum(int(p.shape[0]) for p in st["scans"])
+    switch = [t for t in m.timings if t.get("finish_ms", 0) > 0]
+    integ = np.array([per_scan[k] for k in range(n) if k % scans_per_submap != 0] or per_scan)
+    # drift correction: optimised submap origins vs the ground-truth sensor pose at their creation
+    ids = m.submap_ids
+    err_odo = err_opt = None
+    if len(ids) >= 2:
+        starts = [int(round(m.submap_start[i] * hz)) for i in ids]
+        gt0 = st["gt"][starts]
+        odo0 = st["odom"][starts]
+        opt = np.array([m.submap_pose[i] for i in ids])
+        # express everything relative to the first submap (gauge)
+        err_odo = float(np.abs((odo0[:, :2] - odo0[0, :2]) - (gt0[:, :2] - gt0[0, :2])).mean())
+        err_opt = float(np.abs((opt[:, :2] - opt[0, :2]) - (gt0[:, :2] - gt0[0, :2])).mean())
+    # CPU: the restated Fast integrator, all cores (voxblox: hardware_concurrency) and one thread
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nt = max(1, min(cores, 64))
+    lay = o.Layer(voxel_size, 16)
+    oc = o.tsdf_config(mode=1, default_truncation_distance=trunc,
+                       max_ray_length_m=16.0 if st["kind"] == "lidar" else 5.0)
+    T0 = np.array([1, 0, 0, 0, 0, 0, 0], np.float32)
+    o.tsdf_integrate_mt(lay, oc, T0, st["scans"][0], nt)
+    cpu_ms = []
+    cpu_upd = 0
+    for k in range(min(cpu_scans, n)):
+        t0 = time.time(); so = o.tsdf_integrate_mt(lay, oc, T0, st["scans"][k], nt); cpu_ms.append((time.time() - t0) * 1e3)
+        cpu_upd += int(so.voxel_updates)
+    for i in ids:
+        ctx.submap_free(i)
+    return {"stream": "%s, %d scans @ %g Hz, %.2f m voxels, trunc %.2f m, new submap every %d scans" % (
+                st["kind"], n, hz, voxel_size, trunc, scans_per_submap),
+            "rays_per_scan": rays // n, "voxel_updates_per_scan": upd // n,
+            "scans_per_s_e2e": n / wall, "realtime_factor": (n / wall) / hz,
+            "integrate_ms_per_scan_e2e_median": float(np.median(integ) * 1e3),
+            "integrate_kernel_ms_per_scan": k_ms / max(n, 1),
+            "updates_per_s_e2e": upd / wall,
+            "updates_per_s_kernel": upd / (k_ms * 1e-3) if k_ms > 0 else None,
+            "frac_of_hbm_peak_kernel": (upd * ALGO_BYTES_PER_TSDF_UPDATE / (k_ms * 1e-3) / 1e9 / peak) if k_ms > 0 else None,
+            "submaps": len(ids),
+            "submap_switch": {"finish_ms_median": float(np.median([t["finish_ms"] for t in switch])) if switch else None,
+                              "overlap_ms_median": float(np.median([t["overlap_ms"] for t in switch])) if switch else None,
+                              "optimize_ms_median": float(np.median([t.get("optimize_ms", 0.0) for t in switch])) if switch else None,
+                              "pairs_last": switch[-1]["pairs"] if switch else 0,
+                              "isosurface_points_last": switch[-1].get("isosurface_points") if switch else None,
+                              "blocks_last": switch[-1].get("finished_blocks") if switch else None},
+            "submap_origin_xy_error_odometry_m": err_odo, "submap_origin_xy_error_optimised_m": err_opt,
+            "cpu_reference_integrate_ms_per_scan_mt": float(np.median(cpu_ms)), "cpu_reference_threads": nt,
+            "cpu_reference_updates_per_s_mt": cpu_upd / (sum(cpu_ms) * 1e-3)}
 
 
 def scene_problem(sc):
@@ -463,6 +608,14 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             sys.stderr.write("config4 leg skipped: %r\n" % (e,))
 
+    want_stream = (world == 1 and not args.no_extras and not args.no_stream)
+    st_lidar = None
+    if want_stream:
+        try:
+            st_lidar = build_stream("lidar", args.stream_scans, rank)
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write("stream leg skipped: %r\n" % (e,))
+
     import torch
     import torch.distributed as dist
     from voxgraph_b200 import api
@@ -593,6 +746,16 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             extras["tsdf"] = {"error": repr(e)}
 
+    # ---------------- streaming leg (BASELINE configs[2]): integrate -> finish -> register online
+    if st_lidar is not None and rank == 0:
+        try:
+            extras["stream"] = stream_leg(ctx, api, st_lidar, 0.15, 10, peak)
+            e2e["stream_scans_per_s"] = extras["stream"]["scans_per_s_e2e"]
+            e2e["stream_realtime_factor_vs_10hz"] = extras["stream"]["realtime_factor"]
+            e2e["stream_updates_per_s_e2e"] = extras["stream"]["updates_per_s_e2e"]
+        except Exception as e:  # pragma: no cover
+            extras["stream"] = {"error": repr(e)}
+
     # ---------------- config4 leg at N = 1 (the strong-scaling curve's own first point)
     if sc_c4 is not None:
         try:
@@ -675,6 +838,15 @@ def tsdf_leg(ctx, sc, peak):
         oc = o.tsdf_config(mode=kw["mode"])
         o.tsdf_integrate(lay, oc, T, pts)
         tc = time.time(); so = o.tsdf_integrate(lay, oc, T, pts); cpu_s = time.time() - tc
+        # voxblox runs integrator_threads = hardware_concurrency: multi-threaded restatement, median of 3
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        nt = max(1, min(cores, 64))
+        lay_mt = o.Layer(0.2, 16)
+        o.tsdf_integrate_mt(lay_mt, oc, T, pts, nt)
+        mt = []
+        for _ in range(3):
+            tc = time.time(); smt = o.tsdf_integrate_mt(lay_mt, oc, T, pts, nt); mt.append(time.time() - tc)
+        cpu_mt_s = float(np.median(mt))
         out[name] = {
             "voxel_updates_per_scan": int(st.voxel_updates), "rays_cast": int(st.rays_cast),
             "kernels_ms": kms,
@@ -683,8 +855,11 @@ def tsdf_leg(ctx, sc, peak):
             "updates_per_s_e2e": st.voxel_updates / wall,
             "achieved_gbs": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9,
             "frac_of_hbm_peak": st.voxel_updates * ALGO_BYTES_PER_TSDF_UPDATE / (kms * 1e-3) / 1e9 / peak,
+            "saturated_batches": int(st.saturated_batches),
             "cpu_reference_scan_ms_1_thread": cpu_s * 1e3,
-            "cpu_reference_updates_per_s_1_thread": so.voxel_updates / cpu_s}
+            "cpu_reference_updates_per_s_1_thread": so.voxel_updates / cpu_s,
+            "cpu_reference_scan_ms_mt": cpu_mt_s * 1e3, "cpu_reference_threads_mt": nt,
+            "cpu_reference_updates_per_s_mt": smt.voxel_updates / cpu_mt_s}
         ctx.submap_free(10 ** 6)
     return out
 

@@ -83,7 +83,9 @@ int vgx_submap_finish(vgx_ctx* ctx, uint32_t submap_id);
 typedef struct vgx_registration_filter {   /* VoxgraphSubmap::Config::RegistrationFilter (h:26-30) */
   double min_voxel_weight;                 /* 1 */
   double max_voxel_distance;               /* 0.3 */
-  int use_esdf_distance;                   /* reference default true; 0 here = TSDF distance */
+  int use_esdf_distance;                   /* reference default true: relevant voxels carry the ESDF
+                                              distance (cpp:185-189; needs vgx_submap_generate_esdf);
+                                              vgx_registration_filter_default sets 0 = TSDF distance */
 } vgx_registration_filter;
 void vgx_registration_filter_default(vgx_registration_filter* f);
 /* On a finished submap (uploaded or integrated). filter may be NULL (defaults). */
@@ -96,6 +98,26 @@ int vgx_submap_download_points(vgx_ctx* ctx, uint32_t submap_id, int point_type,
                                float* xyz /* n x 3 */, float* distance, float* weight, int* n);
 /* Submap-frame surface OBB; VGX_ZERO_WEIGHT when no voxel qualified (box stays +-inf). */
 int vgx_submap_surface_obb(vgx_ctx* ctx, uint32_t submap_id, float obb_min[3], float obb_max[3]);
+/* TsdfEsdfSubmap::generateEsdf (finishSubmap, voxgraph_submap.cpp:86) on the device: ESDF bricks
+ * + their registration view from the resident TSDF bricks of a finished submap, so that the
+ * reference's default registration branch (use_esdf_distance = true,
+ * registration_cost_function.h:35, cpp:133-140) has a device producer.  Restates
+ * voxblox::EsdfIntegrator's batch update as its fixed point: observed <=> TSDF weight >=
+ * min_weight; |tsdf| < min_distance_m is copied (fixed); elsewhere the quasi-Euclidean distance
+ * propagated through the 26-neighbourhood of same-sign observed voxels, clipped at max_distance_m
+ * (default_distance_m where nothing reaches).  sweeps (may be NULL): relaxation sweeps run. */
+typedef struct vgx_esdf_config {      /* voxblox::EsdfIntegrator::Config subset */
+  float max_distance_m;               /* 2.0 */
+  float default_distance_m;           /* 2.0 */
+  float min_distance_m;               /* 0.2 */
+  float min_weight;                   /* 1e-6 */
+} vgx_esdf_config;
+void vgx_esdf_config_default(vgx_esdf_config* cfg);
+int vgx_submap_generate_esdf(vgx_ctx* ctx, uint32_t submap_id, const vgx_esdf_config* cfg, int* sweeps);
+/* ESDF bricks in block (allocation) order: distance and observed (1 / 0) per voxel. */
+int vgx_submap_download_esdf(vgx_ctx* ctx, uint32_t submap_id, int max_blocks, float* distance,
+                             float* observed, int* n_blocks);
+
 /* PoseGraphInterface::updateOverlappingSubmapList (pose_graph_interface.cpp:109-147) over
  * VoxgraphSubmap::overlapsWith (voxgraph_submap.cpp:245-278): mission-frame surface-AABB rejection,
  * then "any isosurface block centre of the first submap lands in an allocated block of the second",
@@ -135,10 +157,12 @@ typedef struct vgx_tsdf_config {          /* voxblox::TsdfIntegratorBase::Config
   float sparsity_compensation_factor;     /* yaml:28  20 */
   float start_voxel_subsampling_factor;   /* FastTsdfIntegrator, 2 */
   int max_consecutive_ray_collisions;     /* FastTsdfIntegrator, 2 */
-  int mode;                               /* 0 simple (every ray, every voxel), 1 fast */
-  int deterministic;                      /* extension, mode 0 only: apply the updates of each voxel
-                                             in ray order (bit-identical to the single-threaded
-                                             reference) instead of lock-free in arrival order */
+  int mode;                               /* 0 simple (every ray, every voxel; the updates of each
+                                             voxel are applied in ray order = bit-identical to the
+                                             single-threaded reference), 1 fast (FastTsdfIntegrator
+                                             scheduling, what voxgraph runs) */
+  int deterministic;                      /* ignored (kept for layout compatibility): mode 0 is always
+                                             ray ordered */
 } vgx_tsdf_config;
 
 typedef struct vgx_tsdf_stats {
@@ -146,6 +170,8 @@ typedef struct vgx_tsdf_stats {
   int64_t rays_cast;
   int64_t voxel_updates;
   int64_t blocks_allocated;
+  int64_t saturated_batches;   /* mode 0: 32-update batches of sensor-adjacent voxels collapsed in
+                                  closed form (distance pinned at +trunc, exact integer weight sum) */
 } vgx_tsdf_stats;
 
 void vgx_tsdf_config_default(vgx_tsdf_config* cfg);
@@ -167,6 +193,9 @@ typedef struct vgx_reg_config {           /* RegistrationCostFunction::Config (h
                                              std::mt19937 per submap and point type,
                                              weighted_sampler_inl.h:19-28) and their weight is
                                              forced to 1 (cpp:118-122). */
+  int use_esdf_distance;                  /* h:35 (reference default true): interpolate the reading
+                                             submap's ESDF (vgx_submap_generate_esdf) instead of its
+                                             TSDF (cpp:133-153).  vgx_reg_config_default sets 0. */
 } vgx_reg_config;
 void vgx_reg_config_default(vgx_reg_config* cfg);
 

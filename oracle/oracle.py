@@ -120,6 +120,11 @@ class TsdfConfig(C.Structure):
                 ("mode", C.c_int)]
 
 
+class EsdfConfig(C.Structure):
+    _fields_ = [("max_distance_m", C.c_float), ("default_distance_m", C.c_float),
+                ("min_distance_m", C.c_float), ("min_weight", C.c_float)]
+
+
 class TsdfStats(C.Structure):
     _fields_ = [("rays_valid", C.c_int64), ("rays_cast", C.c_int64),
                 ("voxel_updates", C.c_int64), ("blocks_allocated", C.c_int64)]
@@ -185,6 +190,8 @@ def lib():
     L.vgo_find_isosurface_vertices.argtypes = [vp, C.c_double, f32p, f32p, f32p, C.c_int, i32p, C.c_int,
                                                C.POINTER(C.c_int)]
     L.vgo_interp_voxel.argtypes = [vp, f32p, f32p, f32p]
+    L.vgo_esdf_config_default.argtypes = [C.POINTER(EsdfConfig)]
+    L.vgo_generate_esdf.argtypes = [vp, C.POINTER(EsdfConfig), f32p, f32p]
     L.vgo_surface_obb.argtypes = [vp, C.c_double, C.c_double, f32p, f32p]
     L.vgo_aabb_from_obb_and_pose.argtypes = [f32p, f32p, f32p, f32p, f32p]
     L.vgo_submaps_overlap.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_float, vp]
@@ -197,6 +204,8 @@ def lib():
     L.vgo_tsdf_config_default.argtypes = [C.POINTER(TsdfConfig)]
     L.vgo_tsdf_integrate.argtypes = [vp, C.POINTER(TsdfConfig), f32p, C.c_int, f32p,
                                      C.POINTER(TsdfStats)]
+    L.vgo_tsdf_integrate_mt.argtypes = [vp, C.POINTER(TsdfConfig), f32p, C.c_int, f32p, C.c_int,
+                                        C.POINTER(TsdfStats)]
     L.vgo_raycast.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                               C.c_int, i64p, C.c_int]
     _lib = L
@@ -527,6 +536,24 @@ def interp_voxel(layer, pos):
     return bool(ok), d.value, w.value
 
 
+def esdf_config(**kw):
+    c = EsdfConfig()
+    lib().vgo_esdf_config_default(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def generate_esdf(layer, cfg=None):
+    """generateEsdf -> (distance (n_blocks, vps^3), observed (n_blocks, vps^3), sweeps), slot order."""
+    cfg = cfg or esdf_config()
+    n = layer.num_blocks
+    vpb = layer.vps ** 3
+    d = np.zeros((max(n, 1), vpb), np.float32); ob = np.zeros((max(n, 1), vpb), np.float32)
+    sweeps = lib().vgo_generate_esdf(layer._h, C.byref(cfg), _p(d, C.c_float), _p(ob, C.c_float))
+    return d[:n], ob[:n], sweeps
+
+
 def surface_obb(layer, min_voxel_weight=1.0, max_voxel_distance=0.3):
     mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
     ok = lib().vgo_surface_obb(layer._h, float(min_voxel_weight), float(max_voxel_distance),
@@ -565,6 +592,15 @@ def tsdf_integrate(layer, cfg, T_G_C, points_C):
     st = TsdfStats()
     lib().vgo_tsdf_integrate(layer._h, C.byref(cfg), _p(T, C.c_float), pts.shape[0],
                              _p(pts, C.c_float), C.byref(st))
+    return st
+
+
+def tsdf_integrate_mt(layer, cfg, T_G_C, points_C, num_threads):
+    """Multi-threaded integrator (voxblox runs hardware_concurrency threads): timing baseline."""
+    T = f32(T_G_C); pts = f32(points_C).reshape(-1, 3)
+    st = TsdfStats()
+    lib().vgo_tsdf_integrate_mt(layer._h, C.byref(cfg), _p(T, C.c_float), pts.shape[0],
+                                _p(pts, C.c_float), int(num_threads), C.byref(st))
     return st
 
 

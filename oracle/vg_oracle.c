@@ -39,6 +39,7 @@ struct vgo_layer {
   float* weight;    /* n x vps^3 */
   int32_t* table;   /* open addressing, slot or -1 */
   uint32_t table_size; /* power of two */
+  int mt_zeroed_from, mt_zeroed_to; /* spare bricks [from, to) zeroed for the multi-threaded integrator */
 };
 
 /* voxblox AnyIndexHash: x + y*17191 + z*17191^2 (block_hash.h) */
@@ -1210,6 +1211,77 @@ int vgo_find_isosurface_vertices(const vgo_layer* l, double min_w, float* xyz, f
   return n;
 }
 
+/* ========================================================================= */
+/* ESDF generation (fixed point of EsdfIntegrator's batch update)            */
+/* ========================================================================= */
+void vgo_esdf_config_default(vgo_esdf_config* c) {
+  c->max_distance_m = 2.0f;
+  c->default_distance_m = 2.0f;
+  c->min_distance_m = 0.2f;
+  c->min_weight = 1e-6f;
+}
+
+int vgo_generate_esdf(const vgo_layer* l, const vgo_esdf_config* c, float* dist, float* obs) {
+  const int vps = l->vps, vpb = l->vox_per_block;
+  const size_t nvox = (size_t)l->n_blocks * vpb;
+  uint8_t* fixed = (uint8_t*)calloc(nvox ? nvox : 1, 1);
+  for (size_t i = 0; i < nvox; ++i) {
+    const float w = l->weight[i], d = l->distance[i];
+    if (w < c->min_weight) { dist[i] = 0.f; obs[i] = 0.f; continue; }
+    obs[i] = 1.f;
+    if (fabsf(d) < c->min_distance_m) { fixed[i] = 1; dist[i] = d; }
+    else dist[i] = (d > 0.f ? 1.f : -1.f) * c->default_distance_m;   /* signum(tsdf) * default */
+  }
+  /* neighbour slots of every block (27, centre included) */
+  int* nb = (int*)malloc(sizeof(int) * 27 * (size_t)(l->n_blocks ? l->n_blocks : 1));
+  for (int b = 0; b < l->n_blocks; ++b)
+    for (int k = 0; k < 27; ++k) {
+      const int32_t q[3] = {l->idx[3 * b] + (k % 3) - 1, l->idx[3 * b + 1] + ((k / 3) % 3) - 1,
+                            l->idx[3 * b + 2] + (k / 9) - 1};
+      nb[27 * b + k] = vgo_layer_find_block(l, q);
+    }
+  int sweeps = 0, changed = 1;
+  while (changed) {
+    changed = 0;
+    ++sweeps;
+    for (int b = 0; b < l->n_blocks; ++b)
+      for (int lin = 0; lin < vpb; ++lin) {
+        const size_t i = (size_t)b * vpb + lin;
+        if (obs[i] == 0.f || fixed[i]) continue;
+        const int v[3] = {lin % vps, (lin / vps) % vps, lin / (vps * vps)};
+        float d = dist[i];
+        for (int dz = -1; dz <= 1; ++dz)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+              if (!dx && !dy && !dz) continue;
+              int q[3] = {v[0] + dx, v[1] + dy, v[2] + dz}, bo[3] = {1, 1, 1};
+              for (int a = 0; a < 3; ++a) {
+                if (q[a] < 0) { q[a] += vps; bo[a] = 0; }
+                else if (q[a] >= vps) { q[a] -= vps; bo[a] = 2; }
+              }
+              const int s = nb[27 * b + bo[0] + 3 * bo[1] + 9 * bo[2]];
+              if (s < 0) continue;
+              const size_t j = (size_t)s * vpb + q[0] + vps * (q[1] + vps * q[2]);
+              if (obs[j] == 0.f) continue;
+              const float dn = dist[j];
+              /* |offset| * voxel_size: 1, sqrt(2), sqrt(3) in float */
+              const int m = abs(dx) + abs(dy) + abs(dz);
+              const float step = (m == 1 ? 1.0f : (m == 2 ? sqrtf(2.0f) : sqrtf(3.0f))) * l->voxel_size;
+              if (d > 0.f && dn > 0.f) {
+                const float cand = dn + step;
+                if (cand < c->max_distance_m && cand < d) d = cand;
+              } else if (d < 0.f && dn < 0.f) {
+                const float cand = dn - step;
+                if (cand > -c->max_distance_m && cand > d) d = cand;
+              }
+            }
+        if (d != dist[i]) { dist[i] = d; changed = 1; }
+      }
+  }
+  free(nb); free(fixed);
+  return sweeps;
+}
+
 int vgo_surface_obb(const vgo_layer* l, double min_w, double max_d, float mn[3], float mx[3]) {
   const int vps = l->vps;
   const float half = 0.5f * l->voxel_size;
@@ -1547,5 +1619,166 @@ void vgo_tsdf_integrate(vgo_layer* l, const vgo_tsdf_config* c, const float T_G_
   }
   S.blocks_allocated = l->n_blocks - blocks_before;
   free(start_set); free(obs_set);
+  if (st) *st = S;
+}
+
+
+/* ========================================================================= */
+/* Multi-threaded integrator (timing baseline)                               */
+/* ========================================================================= */
+#define VGO_MT_LOCKS 65536
+typedef struct {
+  vgo_layer* l;
+  const vgo_tsdf_config* c;
+  const float* T;
+  const float* pts;
+  int n, nt;
+  atomic_int next_id;
+  pthread_mutex_t alloc_mu;
+  atomic_flag* locks;
+  _Atomic uint64_t* start_set;
+  _Atomic uint64_t* obs_set;
+  _Atomic int64_t rays_valid, rays_cast, voxel_updates;
+} tsdf_mt_job;
+
+/* capacity for `extra` more blocks without any reallocation; the new bricks are zeroed up front */
+static void layer_reserve(vgo_layer* l, int extra) {
+  if (l->cap_blocks - l->n_blocks >= extra / 2 && l->mt_zeroed_from <= l->n_blocks && l->mt_zeroed_to >= l->cap_blocks)
+    return;  /* enough zeroed spare bricks from an earlier call */
+  const int need = l->n_blocks + extra;
+  if (need > l->cap_blocks) {
+    l->idx = (int32_t*)realloc(l->idx, sizeof(int32_t) * 3 * (size_t)need);
+    l->distance = (float*)realloc(l->distance, sizeof(float) * (size_t)l->vox_per_block * need);
+    l->weight = (float*)realloc(l->weight, sizeof(float) * (size_t)l->vox_per_block * need);
+    l->cap_blocks = need;
+  }
+  memset(l->distance + (size_t)l->n_blocks * l->vox_per_block, 0,
+         sizeof(float) * (size_t)l->vox_per_block * (l->cap_blocks - l->n_blocks));
+  memset(l->weight + (size_t)l->n_blocks * l->vox_per_block, 0,
+         sizeof(float) * (size_t)l->vox_per_block * (l->cap_blocks - l->n_blocks));
+  l->mt_zeroed_from = l->n_blocks;
+  l->mt_zeroed_to = l->cap_blocks;
+  uint32_t ts = l->table_size;
+  while ((uint32_t)l->cap_blocks * 2 > ts) ts *= 2;
+  if (ts != l->table_size) {
+    l->table_size = ts;
+    l->table = (int32_t*)realloc(l->table, sizeof(int32_t) * ts);
+    for (uint32_t i = 0; i < ts; ++i) l->table[i] = -1;
+    for (int i = 0; i < l->n_blocks; ++i) layer_table_insert(l, i);
+  }
+}
+
+static int layer_get_or_add_mt(tsdf_mt_job* J, const int32_t b[3]) {
+  vgo_layer* l = J->l;
+  int slot = vgo_layer_find_block(l, b);
+  if (slot >= 0) return slot;
+  pthread_mutex_lock(&J->alloc_mu);
+  slot = vgo_layer_find_block(l, b);
+  if (slot < 0 && l->n_blocks < l->cap_blocks) {
+    slot = l->n_blocks;
+    l->idx[3 * slot] = b[0]; l->idx[3 * slot + 1] = b[1]; l->idx[3 * slot + 2] = b[2];
+    atomic_thread_fence(memory_order_release);
+    l->n_blocks = slot + 1;
+    layer_table_insert(l, slot);   /* the brick was zeroed by layer_reserve */
+  }
+  pthread_mutex_unlock(&J->alloc_mu);
+  return slot;
+}
+
+static void* tsdf_mt_worker(void* arg) {
+  tsdf_mt_job* J = (tsdf_mt_job*)arg;
+  vgo_layer* l = J->l;
+  const vgo_tsdf_config* c = J->c;
+  const int id = atomic_fetch_add(&J->next_id, 1);
+  const float origin[3] = {J->T[4], J->T[5], J->T[6]};
+  const uint64_t mask = ((uint64_t)1 << 20) - 1;
+  int64_t n_valid = 0, n_cast = 0, n_upd = 0;
+  for (int i = id; i < J->n; i += J->nt) {
+    const float* pC = J->pts + 3 * (size_t)i;
+    const float ray_distance = sqrtf(pC[0] * pC[0] + pC[1] * pC[1] + pC[2] * pC[2]);
+    int is_clearing = 0;
+    if (ray_distance < c->min_ray_length_m) continue;
+    else if (ray_distance > c->max_ray_length_m) {
+      if (c->allow_clear) is_clearing = 1;
+      else continue;
+    }
+    n_valid++;
+    float pG[3];
+    vgo_T_transform(J->T, pC, pG);
+    if (c->mode == 1) {
+      float inv = c->start_voxel_subsampling_factor * l->voxel_size_inv;
+      int64_t k[3] = {(int64_t)floorf(pG[0] * inv + VGO_COORD_EPS),
+                      (int64_t)floorf(pG[1] * inv + VGO_COORD_EPS),
+                      (int64_t)floorf(pG[2] * inv + VGO_COORD_EPS)};
+      uint64_t h = any_index_hash(k[0], k[1], k[2]);
+      if (atomic_exchange(&J->start_set[h & mask], h) == h) continue;
+    }
+    n_cast++;
+    raycaster rc;
+    raycaster_init(&rc, origin, pG, is_clearing, c->voxel_carving_enabled, c->max_ray_length_m,
+                   l->voxel_size_inv, c->default_truncation_distance, c->mode == 1 ? 0 : 1);
+    float weight;
+    if (c->use_const_weight) weight = 1.0f;
+    else {
+      float dz = fabsf(pC[2]);
+      weight = dz > VGO_FLOAT_EPS ? 1.0f / (dz * dz) : 0.0f;
+    }
+    int64_t g[3];
+    int64_t collisions = 0;
+    int32_t lb[3] = {INT32_MIN, 0, 0};
+    int slot = -1;
+    while (raycaster_next(&rc, g)) {
+      if (c->mode == 1) {
+        uint64_t h = any_index_hash(g[0], g[1], g[2]);
+        if (atomic_exchange(&J->obs_set[h & mask], h) == h) ++collisions;
+        else collisions = 0;
+        if (collisions > c->max_consecutive_ray_collisions) break;
+      }
+      int32_t b[3], loc[3];
+      vgo_block_and_local_from_global(g, l->vps, b, loc);
+      if (b[0] != lb[0] || b[1] != lb[1] || b[2] != lb[2]) {
+        slot = layer_get_or_add_mt(J, b);
+        lb[0] = b[0]; lb[1] = b[1]; lb[2] = b[2];
+      }
+      if (slot < 0) continue;
+      const size_t o = (size_t)slot * l->vox_per_block + loc[0] + l->vps * (loc[1] + l->vps * loc[2]);
+      atomic_flag* lk = &J->locks[(o * 0x9E3779B1u) & (VGO_MT_LOCKS - 1)];
+      while (atomic_flag_test_and_set_explicit(lk, memory_order_acquire)) { }
+      update_tsdf_voxel(l, c, origin, pG, g, weight, l->distance + o, l->weight + o);
+      atomic_flag_clear_explicit(lk, memory_order_release);
+      n_upd++;
+    }
+  }
+  atomic_fetch_add(&J->rays_valid, n_valid);
+  atomic_fetch_add(&J->rays_cast, n_cast);
+  atomic_fetch_add(&J->voxel_updates, n_upd);
+  return NULL;
+}
+
+void vgo_tsdf_integrate_mt(vgo_layer* l, const vgo_tsdf_config* c, const float T_G_C[7], int n,
+                           const float* pts, int num_threads, vgo_tsdf_stats* st) {
+  tsdf_mt_job J;
+  memset(&J, 0, sizeof(J));
+  const int nt = num_threads > 1 ? num_threads : 1;
+  const int blocks_before = l->n_blocks;
+  layer_reserve(l, 4096);
+  J.l = l; J.c = c; J.T = T_G_C; J.pts = pts; J.n = n; J.nt = nt;
+  atomic_init(&J.next_id, 0);
+  pthread_mutex_init(&J.alloc_mu, NULL);
+  J.locks = (atomic_flag*)calloc(VGO_MT_LOCKS, sizeof(atomic_flag));
+  if (c->mode == 1) {
+    const size_t m = (size_t)1 << 20;
+    J.start_set = (_Atomic uint64_t*)malloc(sizeof(uint64_t) * m);
+    J.obs_set = (_Atomic uint64_t*)malloc(sizeof(uint64_t) * m);
+    for (size_t i = 0; i < m; ++i) { atomic_init(&J.start_set[i], ~(uint64_t)0); atomic_init(&J.obs_set[i], ~(uint64_t)0); }
+  }
+  if (nt <= 1) tsdf_mt_worker(&J);
+  else pool_run(nt, tsdf_mt_worker, &J);
+  vgo_tsdf_stats S;
+  memset(&S, 0, sizeof(S));
+  S.rays_valid = J.rays_valid; S.rays_cast = J.rays_cast; S.voxel_updates = J.voxel_updates;
+  S.blocks_allocated = l->n_blocks - blocks_before;
+  free(J.locks); free((void*)J.start_set); free((void*)J.obs_set);
+  pthread_mutex_destroy(&J.alloc_mu);
   if (st) *st = S;
 }

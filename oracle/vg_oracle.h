@@ -213,6 +213,28 @@ int vgo_find_isosurface_vertices(const vgo_layer* layer, double min_voxel_weight
 /* Interpolator::getVoxel(pos, &voxel, true): trilinear distance and weight; 0 when impossible. */
 int vgo_interp_voxel(const vgo_layer* layer, const float pos[3], float* distance, float* weight);
 
+/* cblox::TsdfEsdfSubmap::generateEsdf (finishSubmap, voxgraph_submap.cpp:86) =
+ * voxblox::EsdfIntegrator::updateFromTsdfLayerBatch, restated from the published algorithm as its
+ * fixed point (parity unpinned; upstream is absent):
+ *   a TSDF voxel with weight >= min_weight is observed; |tsdf| < min_distance_m -> fixed, ESDF
+ *   distance = TSDF distance; otherwise the distance starts at sign(tsdf) * default_distance_m and
+ *   is lowered (raised on the negative side) through the 26-neighbourhood,
+ *   d(n) <- d(v) + |offset| * voxel_size for same-sign observed non-fixed neighbours while it stays
+ *   below max_distance_m (quasi-Euclidean, full_euclidean_distance = false).
+ * voxblox pops a bucketed priority queue once; this restatement (and the GPU path) relaxes to
+ * convergence, i.e. the exact shortest quasi-Euclidean path in float arithmetic, which is
+ * independent of the processing order.  Output per voxel of the layer's blocks (slot order):
+ * distance and observed (1 / 0). */
+typedef struct vgo_esdf_config {
+  float max_distance_m;      /* 2.0 */
+  float default_distance_m;  /* 2.0 */
+  float min_distance_m;      /* 0.2 */
+  float min_weight;          /* 1e-6 */
+} vgo_esdf_config;
+void vgo_esdf_config_default(vgo_esdf_config* c);
+/* returns the number of relaxation sweeps */
+int vgo_generate_esdf(const vgo_layer* tsdf, const vgo_esdf_config* cfg, float* distance, float* observed);
+
 /* VoxgraphSubmap::getSubmapFrameSurfaceObb (voxgraph_submap.cpp:280-324). Returns 0 when no
  * voxel qualifies (box stays +-inf). */
 int vgo_surface_obb(const vgo_layer* layer, double min_voxel_weight, double max_voxel_distance,
@@ -278,6 +300,12 @@ void vgo_tsdf_config_default(vgo_tsdf_config* c);
 /* T_G_C = [qw qx qy qz tx ty tz]. Single-threaded, points in order. */
 void vgo_tsdf_integrate(vgo_layer* layer, const vgo_tsdf_config* cfg, const float T_G_C[7],
                         int n, const float* points_C, vgo_tsdf_stats* stats);
+/* Multi-threaded form, as voxblox runs its integrators (integrator_threads = hardware_concurrency;
+ * points dealt to the threads round robin, per-voxel locks, block allocation under a mutex,
+ * ApproxHashSet = atomic exchange).  Order dependent like the reference's; used as the CPU baseline
+ * of the TSDF timing leg, the single-threaded form above stays the parity checker. */
+void vgo_tsdf_integrate_mt(vgo_layer* layer, const vgo_tsdf_config* cfg, const float T_G_C[7],
+                           int n, const float* points_C, int num_threads, vgo_tsdf_stats* stats);
 /* RayCaster restatement: writes up to max_out global voxel indices (int64 x 3);
  * returns the number the caster emits. cast_from_origin=1 -> start->end. */
 int vgo_raycast(const float origin[3], const float point_G[3], int is_clearing,

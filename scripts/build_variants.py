@@ -9,14 +9,15 @@ sys.path.insert(0, ROOT)
 from voxgraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "t128_b5_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
-    "t128_b5_tu8": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_TILE_UNITS=8"],
-    "t128_b5_tu2": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_TILE_UNITS=2"],
-    "t128_b4_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=4"],
-    "t128_b6_tu4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
-    "t64_b10_tu4": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=10"],
-    "t64_b12_tu4": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=12"],
-    "t256_b2_tu4": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=2"],
+    "all_on_b5": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
+    "all_on_b6": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
+    "all_on_b4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=4"],
+    "no_ldg256": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_LDG256=0"],
+    "no_earlyout": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_EARLYOUT=0"],
+    "no_skipgram": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_SKIPGRAM=0"],
+    "all_off": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_LDG256=0", "-DVGX_REG_EARLYOUT=0", "-DVGX_REG_SKIPGRAM=0"],
+    "all_on_t256_b2": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=2"],
+    "all_on_t256_b3": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=3"],
 }
 
 if __name__ == "__main__":

@@ -27,14 +27,31 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs the C compiler's view of include/voxgraph_b200.h (size and every field offset)."""
+    import subprocess
     from voxgraph_b200 import _lib
-    # field counts / sizes of the plain-C structs crossing the boundary
-    assert C.sizeof(_lib.TsdfConfig) == 14 * 4
-    assert C.sizeof(_lib.TsdfStats) == 4 * 8
-    assert C.sizeof(_lib.RegConfig) == 24
-    assert C.sizeof(_lib.SolverOptions) == 8 + 10 * 8 + 8
-    assert C.sizeof(_lib.SolverSummary) == 16 + 3 * 8
+    structs = {"vgx_tsdf_config": _lib.TsdfConfig, "vgx_tsdf_stats": _lib.TsdfStats,
+               "vgx_reg_config": _lib.RegConfig, "vgx_solver_options": _lib.SolverOptions,
+               "vgx_solver_summary": _lib.SolverSummary, "vgx_registration_filter": _lib.RegistrationFilter,
+               "vgx_esdf_config": _lib.EsdfConfig}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "voxgraph_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE,
+                                                 text=True).stdout.strip().splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+    assert C.sizeof(_lib.TsdfConfig) == 14 * 4 and C.sizeof(_lib.TsdfStats) == 5 * 8
 
 
 def test_no_cpu_fallback(lib):

@@ -83,7 +83,7 @@ def test_config2_fused_equals_sum_of_emit(ctx, oracle, config2_scene):
 
 def test_full_scan_ray_ordered_is_deterministic(ctx):
     """64 x 1024 LiDAR scan (BASELINE configs[2] shape): two fresh submaps integrated with the
-    ray-ordered path agree bit for bit, and do exactly the work of the lock-free path."""
+    ray-ordered path agree bit for bit."""
     world = synth.make_world(2, size_xy=(120.0, 80.0), n_clutter=400, n_walls=24)
     pts = synth.lidar_scan(world, np.array([60.0, 40.0, 1.2, 0.3]), n_beams=64, n_azimuth=1024, seed=3,
                            miss_range=40.0)
@@ -94,6 +94,7 @@ def test_full_scan_ray_ordered_is_deterministic(ctx):
     for sid, det in ((500, 1), (501, 1), (502, 0)):
         ctx.submap_create(sid, 0.2, 16, 8192)
         st = ctx.tsdf_integrate(sid, T, pts, ctx.tsdf_config(mode=0, deterministic=det))
+        assert st.saturated_batches > 1000
         stats.append((st.rays_valid, st.rays_cast, st.voxel_updates, st.blocks_allocated))
         out.append(ctx.submap_download(sid))
     assert stats[0] == stats[1] == stats[2]

@@ -49,7 +49,7 @@ multi.comm_init(world, rank, uid.cpu().numpy())
 pg2 = build(multi)
 ok, c2, g2, H2 = pg2.evaluate()
 local, glob = multi.graph_num_registration_residuals()
-assert glob == 2 * len(sc.pairs) * 3000 and 0 < local < glob, (local, glob)
+assert glob == 2 * len(sc.pairs) * 3000 and 0 <= local < glob, (local, glob)
 assert abs(c2 - c1) <= 1e-12 * abs(c1), (c1, c2)
 assert np.abs(H2 - H1).max() <= 1e-12 * np.abs(H1).max()
 assert np.abs(g2 - g1).max() <= 1e-12 * np.abs(g1).max()
@@ -67,6 +67,7 @@ assert s2.final_cost < s2.initial_cost
 xt = torch.from_numpy(x2).cuda(); x0 = xt.clone(); dist.broadcast(x0, 0)
 assert torch.equal(xt, x0)                  # all ranks took the same LM decisions
 # ---- NVLink peer-memory exchange (CUDA IPC) instead of NCCL: same answers, bit-identical ranks
+os.environ["VGX_P2P_FUSED"] = "0"           # two launches: assemble (+ push) , wait + local reduce
 peer = api.Context(lr)
 def all_gather_bytes(h):
     t = torch.from_numpy(h).cuda()
@@ -88,8 +89,9 @@ x3 = np.array([pg3.getSubmapPoses()[i] for i in range(len(sc.submaps))])
 assert np.abs(x1 - x3).max() < 1e-6, np.abs(x1 - x3).max()
 xt = torch.from_numpy(x3).cuda(); x0 = xt.clone(); dist.broadcast(x0, 0)
 assert torch.equal(xt, x0)
-# ---- one-launch variant: assemble + signal + wait + gather-sum fused in a persistent kernel
-os.environ["VGX_P2P_FUSED"] = "1"
+# ---- one-launch variant (the default): assemble + push + signal + wait + local reduce fused in a
+#      persistent kernel
+os.environ.pop("VGX_P2P_FUSED", None)
 fused = api.Context(lr)
 api.p2p_setup(fused, world, rank, all_gather_bytes, capacity_doubles=1 << 16)
 pg4 = build(fused)
@@ -100,7 +102,19 @@ pg4.solver_options = fused.solver_options(**opts)
 s4 = pg4.optimize()
 x4 = np.array([pg4.getSubmapPoses()[i] for i in range(len(sc.submaps))])
 assert np.array_equal(x4, x3) and s4.iterations == s3.iterations
-os.environ["VGX_P2P_FUSED"] = "0"
+# ---- self-check used by bench.py: the suspended communicator evaluates the full problem locally
+pg4._sync(); fused.graph_set_poses(np.array([sc.poses_init[i] for i in range(len(sc.submaps))]))
+ok, c5, g5, H5 = pg4.evaluate()
+dist.barrier()
+if rank == 0:
+    fused.comm_suspend(True)
+    ok, c6, g6, H6 = pg4.evaluate()
+    fused.comm_suspend(False)
+    assert abs(c6 - c5) <= 1e-12 * abs(c5) and np.abs(H6 - H5).max() <= 1e-12 * np.abs(H5).max()
+    loc6, glob6 = fused.graph_num_registration_residuals()
+dist.barrier()
+ok, c7, g7, H7 = pg4.evaluate()
+assert c7 == c5 and np.array_equal(H7, H5)
 fused.close()
 dist.barrier()
 sys.stdout.write("rank-%d-multirank-ok %d %d %d %d\n" % (rank, local, glob, s2.iterations, s3.iterations)); sys.stdout.flush()
@@ -109,16 +123,18 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_nccl_allreduce_matches_single(tmp_path):
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_multi_gpu_exchange_matches_single(tmp_path, nproc):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     env = dict(os.environ, VGX_ROOT=ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
     p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-4000:]
-    assert "rank-0-multirank-ok" in p.stdout and "rank-1-multirank-ok" in p.stdout, p.stdout[-4000:]
+    for r in range(nproc):
+        assert ("rank-%d-multirank-ok" % r) in p.stdout, p.stdout[-4000:]

@@ -70,16 +70,15 @@ def test_single_carving_ray_bit_exact(ctx, oracle):
 
 
 def test_lidar_scan_vs_oracle(ctx, oracle):
-    """Dense scan (config-3 shaped, scaled down): identical block set, identical visited-voxel
-    set and update count; weights equal up to float summation order; distances equal except
-    where the reference itself is order dependent (clamped running average)."""
+    """Dense scan (config-3 shaped, scaled down), Simple scheduling: identical block set, identical
+    visited-voxel set, update count, distances and weights (mode 0 is always ray ordered)."""
     world = synth.make_world(3, size_xy=(30.0, 30.0), n_clutter=40, n_walls=4)
     pose = np.array([15.0, 15.0, 1.2, 0.4])
     pts = synth.lidar_scan(world, pose, n_beams=32, n_azimuth=512, seed=1, miss_range=40.0)
     assert pts.shape[0] == 32 * 512
     T = synth.pose_to_T([0.3, -0.2, 0.1, 0.4])
     gcfg, ocfg = _cfg_pair(ctx, oracle)
-    gcfg.deterministic = 0          # lock-free arrival-order path
+    gcfg.deterministic = 0          # ignored: kept in the struct for layout compatibility
     layer = oracle.Layer(VS, 16)
     so = oracle.tsdf_integrate(layer, ocfg, T, pts)
     ctx.submap_create(302, VS, 16, 4096)
@@ -88,21 +87,10 @@ def test_lidar_scan_vs_oracle(ctx, oracle):
     assert ctx.submap_block_count(302) == layer.num_blocks
     go = _as_dict(*layer.export()); gg = _as_dict(*ctx.submap_download(302))
     assert set(go) == set(gg)
-    do = np.stack([go[b][0] for b in go]); wo = np.stack([go[b][1] for b in go])
-    dg = np.stack([gg[b][0] for b in go]); wg = np.stack([gg[b][1] for b in go])
-    assert np.array_equal(wo > 0, wg > 0)             # visited sets identical (indices bit-exact)
-    obs = wo > 0
-    np.testing.assert_allclose(wg[obs], wo[obs], rtol=2e-5)
-    err = np.abs(dg[obs] - do[obs])
-    trunc = 0.6
-    # The clamped running average of updateTsdfVoxel is order dependent (the reference's own
-    # multi-threaded integrators differ run to run on voxels that mix free-space and surface
-    # updates), so only the bulk is compared; the deterministic mode is checked bit-exactly below.
-    assert err.max() <= 2 * trunc
-    print("tsdf dense-scan |d_gpu - d_oracle| percentiles 50/90/99/max:",
-          np.percentile(err, [50, 90, 99]), err.max(), "frac<1e-4:", (err < 1e-4).mean())
-    assert np.median(err) < 1e-6
-    assert (err < 1e-4).mean() > 0.8
+    for b in go:
+        assert np.array_equal(go[b][0], gg[b][0]) and np.array_equal(go[b][1], gg[b][1])
+    # the voxels around the sensor collect one update per ray: their replay collapses in closed form
+    assert sg.saturated_batches > 100
     # finishing the submap builds the registration view; re-integration is refused
     from voxgraph_b200 import api
     ctx.submap_finish(302)
@@ -116,10 +104,10 @@ def test_deterministic_mode_bit_exact_dense_scans(ctx, oracle):
     voxel of every block."""
     world = synth.make_world(3, size_xy=(30.0, 30.0), n_clutter=40, n_walls=4)
     gcfg, ocfg = _cfg_pair(ctx, oracle)
-    gcfg.deterministic = 1
     layer = oracle.Layer(VS, 16)
     ctx.submap_create(310, VS, 16, 4096)
     tot_g = tot_o = 0
+    n_sat = 0
     for k, (px, py, yaw) in enumerate([(15.0, 15.0, 0.4), (16.5, 14.0, 1.9), (13.0, 16.0, -2.6)]):
         pts = synth.lidar_scan(world, np.array([px, py, 1.2, yaw]), n_beams=32, n_azimuth=512, seed=k,
                                miss_range=40.0 if k != 1 else None)
@@ -128,7 +116,9 @@ def test_deterministic_mode_bit_exact_dense_scans(ctx, oracle):
         sg = ctx.tsdf_integrate(310, T, pts, gcfg)
         assert (sg.rays_valid, sg.voxel_updates) == (so.rays_valid, so.voxel_updates)
         tot_g += sg.voxel_updates; tot_o += so.voxel_updates
+        n_sat += sg.saturated_batches
     assert tot_g == tot_o > 500000
+    assert n_sat > 300      # the closed-form replay of saturated batches was exercised
     go = _as_dict(*layer.export()); gg = _as_dict(*ctx.submap_download(310))
     assert set(go) == set(gg)
     for b in go:
@@ -147,7 +137,8 @@ def test_fast_mode_properties(ctx, oracle):
     s_fast = ctx.tsdf_integrate(304, T, pts, ctx.tsdf_config(mode=1))
     assert s_fast.rays_valid == s_simple.rays_valid
     assert s_fast.rays_cast < s_simple.rays_cast and s_fast.voxel_updates < s_simple.voxel_updates
-    so = oracle.tsdf_integrate(oracle.Layer(VS, 16), oracle.tsdf_config(mode=1), T, pts)
+    lay_fast = oracle.Layer(VS, 16)
+    so = oracle.tsdf_integrate(lay_fast, oracle.tsdf_config(mode=1), T, pts)
     # same order of magnitude of work as the single-threaded restatement of the Fast rule
     assert 0.5 * so.voxel_updates < s_fast.voxel_updates < 2.0 * so.voxel_updates
     gs = _as_dict(*ctx.submap_download(303)); gf = _as_dict(*ctx.submap_download(304))
@@ -157,6 +148,46 @@ def test_fast_mode_properties(ctx, oracle):
         m = (gf[b][1] > 0) & (np.abs(gf[b][0]) < 0.3) & (gs[b][1] > 0)
         agree += (np.sign(gf[b][0][m]) == np.sign(gs[b][0][m])).sum(); tot += m.sum()
     assert tot > 100 and agree / tot > 0.9
+    # blocks are allocated on demand, only where a voxel is actually visited (as
+    # allocateStorageAndGetVoxelPtr does; a visit whose update weight drops to zero still allocates):
+    # a subset of the Simple set, and about as many as the single-threaded restatement of the Fast
+    # rule allocates
+    assert sum((gf[b][1] > 0).any() for b in gf) >= 0.9 * len(gf)
+    assert len(gf) <= len(gs)
+    go = _as_dict(*lay_fast.export())
+    assert abs(len(gf) - len(go)) <= 0.1 * len(go)
+    assert len(set(gf) & set(go)) >= 0.85 * len(go)
+
+
+def test_fast_mode_sparse_rays_match_oracle_exactly(ctx, oracle):
+    """Rays that share no voxel and no de-duplication bucket make the Fast schedule deterministic:
+    block set, visited voxels, distances and weights equal the oracle's Fast restatement."""
+    rs = np.random.RandomState(5)
+    dirs = []
+    for az in np.linspace(-3.0, 3.0, 24):
+        for el in (-0.5, 0.0, 0.45):
+            dirs.append([np.cos(az) * np.cos(el), np.sin(az) * np.cos(el), np.sin(el)])
+    pts = (np.array(dirs) * rs.uniform(4.0, 9.0, (len(dirs), 1))).astype(np.float32)
+    T = synth.pose_to_T([0.13, -0.27, 0.31, 0.2])
+    lay = oracle.Layer(VS, 16)
+    so = oracle.tsdf_integrate(lay, oracle.tsdf_config(mode=1), T, pts)
+    ctx.submap_create(308, VS, 16, 4096)
+    sg = ctx.tsdf_integrate(308, T, pts, ctx.tsdf_config(mode=1))
+    go = _as_dict(*lay.export()); gg = _as_dict(*ctx.submap_download(308))
+    # rays leave the sensor through shared voxels, where the race-free schedules may differ: compare
+    # beyond 1.5 m from the sensor origin only (no voxel is shared there)
+    assert (sg.rays_valid, sg.rays_cast) == (so.rays_valid, so.rays_cast)
+    assert set(gg) == set(go)
+    origin = np.array([0.13, -0.27, 0.31])
+    checked = 0
+    for b in go:
+        lin = np.arange(16 ** 3)
+        c = (np.stack([lin % 16, (lin // 16) % 16, lin // 256], -1) + 0.5) * VS + np.array(b) * 16 * VS
+        far = np.linalg.norm(c - origin, axis=1) > 1.5
+        assert np.array_equal(go[b][1][far] > 0, gg[b][1][far] > 0)
+        assert np.array_equal(go[b][0][far], gg[b][0][far]) and np.array_equal(go[b][1][far], gg[b][1][far])
+        checked += int((go[b][1][far] > 0).sum())
+    assert checked > 500
 
 
 def test_capacity_overflow_reports_error(ctx):
@@ -166,6 +197,18 @@ def test_capacity_overflow_reports_error(ctx):
     with pytest.raises(api.VgxError) as e:
         ctx.tsdf_integrate(305, IDENT, pts, ctx.tsdf_config())
     assert e.value.code == -6
+    # the overflow leaves a consistent submap behind (hash rebuilt from the blocks that exist):
+    # further calls keep failing cleanly instead of hanging on a full table, in both modes
+    assert ctx.submap_block_count(305) == 2
+    for mode in (1, 0, 1):
+        with pytest.raises(api.VgxError) as e:
+            ctx.tsdf_integrate(305, IDENT, pts, ctx.tsdf_config(mode=mode))
+        assert e.value.code == -6
+    far = np.array([[60.0, 3.0, 1.0], [-70.0, 2.0, 0.5], [5.0, 80.0, 9.0]], np.float32)
+    with pytest.raises(api.VgxError):
+        ctx.tsdf_integrate(305, IDENT, far, ctx.tsdf_config(mode=1, max_ray_length_m=100.0))
+    idx, d, w = ctx.submap_download(305)
+    assert idx.shape[0] == 2
 
 
 def test_integrate_then_register(ctx, oracle):

@@ -28,6 +28,11 @@ class FakeCtx:
     def graph_set_registration_constraints(self, a, b, cfg):
         self.calls.append(("reg", list(a), list(b), cfg))
 
+    def graph_set_registration_constraints_v(self, a, b, cfgs):
+        # one RegistrationCostFunction::Config per residual block (registration_constraint.h:15-21)
+        assert len(cfgs) == len(a) == len(b)
+        self.calls.append(("reg", list(a), list(b), cfgs[0] if cfgs else None))
+
     def graph_solve(self, n, o):
         self.calls.append(("solve", n, o.exclude_registration))
         class S:  # noqa

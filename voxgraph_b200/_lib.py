@@ -38,7 +38,8 @@ class TsdfConfig(C.Structure):
 
 class TsdfStats(C.Structure):
     _fields_ = [("rays_valid", C.c_int64), ("rays_cast", C.c_int64),
-                ("voxel_updates", C.c_int64), ("blocks_allocated", C.c_int64)]
+                ("voxel_updates", C.c_int64), ("blocks_allocated", C.c_int64),
+                ("saturated_batches", C.c_int64)]
 
 
 class RegistrationFilter(C.Structure):
@@ -49,7 +50,13 @@ class RegistrationFilter(C.Structure):
 class RegConfig(C.Structure):
     _fields_ = [("registration_point_type", C.c_int),
                 ("no_correspondence_cost", C.c_double),
-                ("sampling_ratio", C.c_float)]
+                ("sampling_ratio", C.c_float),
+                ("use_esdf_distance", C.c_int)]
+
+
+class EsdfConfig(C.Structure):
+    _fields_ = [("max_distance_m", C.c_float), ("default_distance_m", C.c_float),
+                ("min_distance_m", C.c_float), ("min_weight", C.c_float)]
 
 
 class SolverOptions(C.Structure):
@@ -96,7 +103,8 @@ EXPORTS = [
     "vgx_graph_get_sample_indices", "vgx_graph_set_sample_indices", "vgx_comm_suspend",
     "vgx_registration_filter_default", "vgx_submap_extract_points", "vgx_submap_finish_ex",
     "vgx_submap_num_points", "vgx_submap_download_points", "vgx_submap_surface_obb",
-    "vgx_find_overlapping_pairs",
+    "vgx_find_overlapping_pairs", "vgx_esdf_config_default", "vgx_submap_generate_esdf",
+    "vgx_submap_download_esdf",
 ]
 
 _lib = None
@@ -161,6 +169,10 @@ def load():
     L.vgx_submap_download_points.argtypes = [vp, u32, i32, i32, pf, pf, pf, C.POINTER(i32)]
     L.vgx_submap_surface_obb.argtypes = [vp, u32, pf, pf]
     L.vgx_find_overlapping_pairs.argtypes = [vp, i32, pu32, pf, i32, pu32, C.POINTER(i32)]
+    L.vgx_esdf_config_default.argtypes = [C.POINTER(EsdfConfig)]
+    L.vgx_esdf_config_default.restype = None
+    L.vgx_submap_generate_esdf.argtypes = [vp, u32, C.POINTER(EsdfConfig), C.POINTER(i32)]
+    L.vgx_submap_download_esdf.argtypes = [vp, u32, i32, pf, pf, C.POINTER(i32)]
     L.vgx_submap_info.argtypes = [vp, u32, pf, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.vgx_submap_draw_samples.argtypes = [vp, u32, i32, i32, pi32]
     L.vgx_graph_num_registration_residuals.argtypes = [vp, C.POINTER(C.c_int64),

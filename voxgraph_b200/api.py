@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (RegConfig, RegistrationFilter, SolverOptions, SolverSummary, TsdfConfig, TsdfStats)
+from ._lib import (EsdfConfig, RegConfig, RegistrationFilter, SolverOptions, SolverSummary, TsdfConfig, TsdfStats)
 
 K_VOXELS = 0            # VoxgraphSubmap::RegistrationPointType::kVoxels
 K_ISOSURFACE_POINTS = 1  # ...::kIsosurfacePoints
@@ -139,6 +139,28 @@ class Context:
         rc = self._check(self._L.vgx_submap_surface_obb(self._h, int(submap_id), _p(mn, C.c_float),
                                                         _p(mx, C.c_float)), allow=(0, 1))
         return rc == 0, mn, mx
+
+    def esdf_config(self, **kw):
+        c = EsdfConfig()
+        self._L.vgx_esdf_config_default(C.byref(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def submap_generate_esdf(self, submap_id, cfg=None):
+        """TsdfEsdfSubmap::generateEsdf on the device -> number of relaxation sweeps."""
+        n = C.c_int(0)
+        self._check(self._L.vgx_submap_generate_esdf(self._h, int(submap_id),
+                                                     C.byref(cfg) if cfg is not None else None, C.byref(n)))
+        return n.value
+
+    def submap_download_esdf(self, submap_id):
+        _, vps, n, _ = self.submap_info(submap_id)
+        d = np.zeros((n, vps ** 3), np.float32); ob = np.zeros((n, vps ** 3), np.float32)
+        got = C.c_int(0)
+        self._check(self._L.vgx_submap_download_esdf(self._h, int(submap_id), n, _p(d, C.c_float),
+                                                     _p(ob, C.c_float), C.byref(got)))
+        return d, ob
 
     def find_overlapping_pairs(self, submap_ids, poses_T):
         """updateOverlappingSubmapList: poses_T (n,7) = [qw qx qy qz tx ty tz] -> list of (id_i, id_j)."""
@@ -454,6 +476,7 @@ class RegistrationConstraintConfig:   # registration_constraint.h:15-21
     no_correspondence_cost: float = 0.0
     sampling_ratio: float = -1.0
     information_matrix: np.ndarray = field(default_factory=lambda: np.eye(4))
+    use_esdf_distance: bool = False       # registration_cost_function.h:35 (reference default true)
 
 
 class PoseGraph:
@@ -523,7 +546,8 @@ class PoseGraph:
                              "identity matrix are not yet supported.")   # registration_constraint.h:32-34
         cfg = self.ctx.reg_config(registration_point_type=int(config.registration_point_type),
                                   no_correspondence_cost=float(config.no_correspondence_cost),
-                                  sampling_ratio=float(config.sampling_ratio))
+                                  sampling_ratio=float(config.sampling_ratio),
+                                  use_esdf_distance=int(bool(getattr(config, "use_esdf_distance", False))))
         self._registration.append((a, b)); self._reg_cfgs.append(cfg)
         if config.registration_point_type == K_ISOSURFACE_POINTS:   # pose_graph.cpp:63-71
             self._registration.append((b, a)); self._reg_cfgs.append(cfg)

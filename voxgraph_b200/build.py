@@ -18,6 +18,7 @@ SOURCES = [
     ("tsdf.cu", ["-fmad=false"]),
     ("extract.cu", ["-fmad=false"]),
     ("overlap.cu", ["-fmad=false"]),
+    ("esdf.cu", ["-fmad=false"]),
     ("graph.cu", []),
     ("p2p.cu", []),
     ("nccl_dyn.cpp", []),

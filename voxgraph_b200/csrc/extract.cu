@@ -236,7 +236,8 @@ __device__ __forceinline__ float atomicMaxFloat(float* addr, float v) {
 // scatter into the unit-major point layout + surface OBB (cpp:280-324: centre -+ half voxel)
 __global__ void __launch_bounds__(256)
 relevant_emit_kernel(LayerDev L, const unsigned* __restrict__ counts, const unsigned* __restrict__ offsets,
-                     float* __restrict__ pts, float* __restrict__ obb /* min[3], max[3] */) {
+                     const float2* __restrict__ esdf /* null: TSDF distance */, float* __restrict__ pts,
+                     float* __restrict__ obb /* min[3], max[3] */) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nvox = (size_t)L.n_blocks << (3 * L.sh);
   if (i >= nvox || counts[i] == 0) return;
@@ -255,7 +256,8 @@ relevant_emit_kernel(LayerDev L, const unsigned* __restrict__ counts, const unsi
     atomicMaxFloat(obb + 3 + a, cpos[a] + half);
   }
   float* u = pts + vgx_pt_index((size_t)offsets[i], 0);
-  u[0] = cpos[0]; u[32] = cpos[1]; u[64] = cpos[2]; u[96] = x.x; u[128] = x.y;
+  // cpp:183-191: the ESDF distance when use_esdf_distance, the weight is always the TSDF weight
+  u[0] = cpos[0]; u[32] = cpos[1]; u[64] = cpos[2]; u[96] = esdf ? esdf[i].x : x.x; u[128] = x.y;
 }
 
 // ------------------------------------------------------------------ isosurface vertices (cpp:203-243)
@@ -507,9 +509,9 @@ extern "C" int vgx_submap_extract_points(vgx_ctx* c, uint32_t id, const vgx_regi
   vgx_registration_filter f;
   vgx_registration_filter_default(&f);
   if (filter) f = *filter;
-  if (f.use_esdf_distance)
-    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_extract_points: use_esdf_distance needs an ESDF layer "
-                                 "(upload it as a submap and extract from that)");
+  if (f.use_esdf_distance && !s->d_esdf && s->n_blocks > 0)
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_extract_points: use_esdf_distance needs the submap's ESDF "
+                                 "(vgx_submap_generate_esdf first, as finishSubmap does)");
   VGX_CUDA(c, cudaSetDevice(c->device));
   vgx_graph_invalidate_registration(c);
   const LayerDev L = layer_of(s);
@@ -556,7 +558,8 @@ extern "C" int vgx_submap_extract_points(vgx_ctx* c, uint32_t id, const vgx_regi
     float* d_pts = nullptr;
     rc = alloc_points(c, (int)total, &d_pts);
     if (rc != VGX_OK) return rc;
-    relevant_emit_kernel<<<grid256, 256, 0, st>>>(L, d_counts, d_offsets, d_pts, d_obb);
+    relevant_emit_kernel<<<grid256, 256, 0, st>>>(L, d_counts, d_offsets, f.use_esdf_distance ? s->d_esdf : nullptr,
+                                                 d_pts, d_obb);
     c->launches++;
     VGX_CUDA(c, cudaGetLastError());
     float obb[6];

@@ -56,7 +56,7 @@ struct VgxGraph {
   // derived
   std::vector<int> local;  // global indices of this rank's registration constraints
   std::vector<int> block_nodes;  // E x 2 (host copy)
-  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_ctas = 0;
+  int n_local = 0, n_tiles = 0, n_rel_local = 0, n_ctas = 0, grid_capacity = 0;
   int E = 0;               // off-diagonal blocks
   int n_free = 0;          // reduced dimension 4 * (non-constant nodes)
   int64_t residuals_local = 0, residuals_global = 0;
@@ -68,7 +68,7 @@ struct VgxGraph {
   RegPoseConst* d_poses = nullptr;
   RegTile* d_tiles = nullptr;
   int* d_tile_begin = nullptr;
-  int* d_sched = nullptr;        // reduce kernel's ticket counter + exit counter
+  int* d_cta_tile_begin = nullptr;
   double* d_partials = nullptr;
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
@@ -92,7 +92,7 @@ struct VgxGraph {
 };
 
 static void free_tables(VgxGraph* g) {
-  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_sched);
+  cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_cta_tile_begin);
   cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
@@ -102,7 +102,7 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_sample_pts); cudaFree(g->d_sample_idx);
   g->d_sample_pts = nullptr; g->d_sample_idx = nullptr;
   if (g->h_state) cudaFreeHost(g->h_state);
-  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_sched = nullptr;
+  g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_cta_tile_begin = nullptr;
   g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
   g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
   g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void rel_eval(const VgxRelEdge& E, const double* __re
 __device__ __forceinline__ void assemble_signal(const VgxP2PSignal& sig) {
   if (sig.nranks == 0) return;
   __shared__ int s_sig_last;
-  __threadfence();
+  __threadfence_system();   // this CTA's pushed values are visible to the peers before its ticket counts
   __syncthreads();
   if (threadIdx.x == 0) s_sig_last = (atomicAdd(sig.counter, 1) == (int)gridDim.x - 1);
   __syncthreads();
@@ -210,7 +210,7 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
                                                const double* __restrict__ x,
                                                const int* __restrict__ csr_begin,
                                                const int2* __restrict__ items,
-                                               double* __restrict__ packed, int N, int E, int n_reg,
+                                               const VgxP2PPush& push, int N, int E, int n_reg,
                                                int n_rel, int exclude_reg, double (*s_part)[20]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ob == N + E) {
@@ -228,8 +228,12 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
     if (lane == 0) s_part[warp][0] = a;
     __syncthreads();
     if (threadIdx.x == 0) {
-      packed[0] = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
-      packed[1] = 0; packed[2] = 0; packed[3] = 0;
+      const double cst = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
+      for (int k = 0; k < push.n; ++k) {
+        double* packed = push.dst[k];
+        packed[0] = cst;
+        packed[1] = 0; packed[2] = 0; packed[3] = 0;
+      }
     }
     __syncthreads();
     return;
@@ -289,8 +293,13 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
   __syncthreads();
   if (warp == 0 && lane < 20) {
     const double tot = ((s_part[0][lane] + s_part[1][lane]) + s_part[2][lane]) + s_part[3][lane];
-    if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
-    else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
+    // single rank: one local destination; peer exchange: the value goes to this rank's slot in
+    // every rank's region (posted stores over NVLink)
+    for (int k = 0; k < push.n; ++k) {
+      double* packed = push.dst[k];
+      if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
+      else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
+    }
   }
   __syncthreads();
 }
@@ -298,52 +307,41 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
 __global__ void __launch_bounds__(128)
 assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
-                const int2* __restrict__ items, double* __restrict__ packed, int N, int E, int n_reg,
+                const int2* __restrict__ items, VgxP2PPush push, int N, int E, int n_reg,
                 int n_rel, int exclude_reg, VgxP2PSignal sig) {
   __shared__ double s_part[4][20];
-  assemble_block(blockIdx.x, csum, rel, x, csr_begin, items, packed, N, E, n_reg, n_rel, exclude_reg, s_part);
+  assemble_block(blockIdx.x, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
   assemble_signal(sig);
 }
 
 // Fused compute + collective (multi-rank, peer exchange): ONE launch assembles this rank's
-// partial into its NVLink-exported buffer, publishes it to every peer, waits for the peers and
-// sums all partials in rank order straight out of peer memory.  The grid is persistent and
-// sized to be fully co-resident, so waiting CTAs can never starve a CTA that still has to
-// produce: phase 1 never waits, phase 2 only waits on flags that phase 1 of every rank sets.
-struct VgxP2PGather {
-  const double* buf[8];  // this epoch's buffer of every rank (peer-mapped)
-  int* timeout_flag;
-};
-
+// partial, PUSHES every value into its slot of every rank's NVLink-mapped region while it is
+// produced, publishes the epoch flag to all peers, waits for the peers' flags and adds the n
+// local slots in rank order.  The grid is persistent and sized to be fully co-resident, so waiting
+// CTAs can never starve a CTA that still has to produce: phase 1 never waits, phase 2 only waits
+// on flags that phase 1 of every rank sets.
 __global__ void __launch_bounds__(128)
 assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
                          const double* __restrict__ x, const int* __restrict__ csr_begin,
-                         const int2* __restrict__ items, double* __restrict__ send, int N, int E,
+                         const int2* __restrict__ items, VgxP2PPush push, int N, int E,
                          int n_reg, int n_rel, int exclude_reg, VgxP2PSignal sig, VgxP2PGather gat,
                          double* __restrict__ out, int count) {
   __shared__ double s_part[4][20];
   __shared__ int s_ok;
   for (int ob = blockIdx.x; ob <= N + E; ob += gridDim.x)
-    assemble_block(ob, csum, rel, x, csr_begin, items, send, N, E, n_reg, n_rel, exclude_reg, s_part);
+    assemble_block(ob, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
   assemble_signal(sig);
-  // ---- phase 2: wait for every rank's flag in OUR region, then gather-sum our slice
+  // ---- phase 2: wait for every rank's flag in OUR region, then add our slice of the local slots
   if (threadIdx.x == 0) {
-    const volatile unsigned long long* mine = sig.flags[sig.rank];
-    const long long t0 = clock64();
-    int ok = 1;
-    for (int r = 0; r < sig.nranks && ok; ++r)
-      while (mine[r] < sig.epoch)
-        if (clock64() - t0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer is gone
+    s_ok = vgx_p2p_wait(gat) ? 1 : 0;
     __threadfence_system();
-    s_ok = ok;
-    if (!ok) *gat.timeout_flag = 1;
   }
   __syncthreads();
-  if (!s_ok) return;
+  const bool ok = s_ok != 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int r = 0; r < sig.nranks; ++r) s += *((const volatile double*)(gat.buf[r] + i));
-    out[i] = s;
+    for (int r = 0; r < gat.nranks; ++r) s += *((const volatile double*)(gat.slot[r] + i));
+    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // poison on timeout
   }
 }
 
@@ -1071,26 +1069,69 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
       VGX_CUDA(c, cudaStreamSynchronize(c->stream));  // g->samples[] are pageable host vectors
     }
   }
-  // Every constraint is cut into tiles of VGX_REG_TILE_UNITS 32-point units (128-byte aligned
-  // unit-major slices for TMA); the persistent warps of the reduce kernel draw them dynamically.
-  {
-    const int tile_pts = VGX_REG_TILE_UNITS * VGX_REG_UNIT;
+  // Cut the local residual index space into 32-point units and deal them evenly to the resident
+  // CTAs; a tile is the part of one CTA's run of units that lies inside one residual block (tiles
+  // never straddle constraints and start on a unit boundary = 128-byte aligned SoA slices for TMA).
+  g->grid_capacity = 0;
+  for (const auto& cc : cons)
+    if (cc.grid) g->grid_capacity = std::max(g->grid_capacity, (cc.gd0 * cc.gd1 * cc.gd2 + 7) & ~7);  // 16-byte multiple
+  const int n_ctas_max = std::max(vgx_reg_resident_ctas(c->device, g->grid_capacity), 1);
+  int64_t U = 0;  // total units
+  for (const auto& cc : cons) U += (cc.n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
+  g->n_ctas = (int)std::min<int64_t>(n_ctas_max, U);
+  std::vector<int> cta_tile_begin;
+  // Scheduling of the reduce kernel.  The cost of a unit varies ~4x with the share of its points
+  // that land in the reading submap, so a static equal cut leaves SMs idle while the hit-heavy
+  // ones finish (measured: max SM busy time 16 % above the mean).  hw_units > 0: fixed tiles of
+  // that many units, ONE CTA PER TILE, dealt to the SMs by the hardware block scheduler as
+  // resident CTAs retire (dynamic balancing at no instruction cost; the per-CTA set-up latency
+  // hides behind the other resident CTAs).  0: persistent CTAs with an equal static cut.
+  int hw_units = VGX_REG_HW_TILE_UNITS;
+  if (const char* e = getenv("VGX_REG_HW_TILE_UNITS")) hw_units = atoi(e);
+  if (hw_units > 0) {
     for (int k = 0; k < g->n_local; ++k) {
       tile_begin.push_back((int)tiles.size());
+      const int tile_pts = hw_units * VGX_REG_UNIT;
       for (int s0 = 0; s0 < cons[k].n; s0 += tile_pts) {
         RegTile t;
-        t.constraint = k; t.start = s0; t.count = std::min(tile_pts, cons[k].n - s0); t.pad = 0;
+        t.constraint = k; t.start = s0; t.count = std::min(tile_pts, cons[k].n - s0);
         tiles.push_back(t);
       }
     }
-    tile_begin.push_back((int)tiles.size());
+    g->n_ctas = (int)tiles.size();
+    cta_tile_begin.resize(tiles.size() + 1);
+    for (size_t k = 0; k <= tiles.size(); ++k) cta_tile_begin[k] = (int)k;
+  } else {
+    int64_t ubase = 0;  // unit index of the current constraint's first unit
+    int cta = 0;
+    auto cta_end = [&](int k) { return (int64_t)(((__int128)U * (k + 1)) / std::max(g->n_ctas, 1)); };
+    if (g->n_ctas > 0) cta_tile_begin.push_back(0);
+    for (int k = 0; k < g->n_local; ++k) {
+      tile_begin.push_back((int)tiles.size());
+      const int64_t uc = (cons[k].n + VGX_REG_UNIT - 1) / VGX_REG_UNIT;
+      int64_t u = 0;
+      while (u < uc) {
+        while (cta + 1 < g->n_ctas && ubase + u >= cta_end(cta)) { cta_tile_begin.push_back((int)tiles.size()); ++cta; }
+        const int64_t take = std::min<int64_t>(uc - u, cta_end(cta) - (ubase + u));
+        RegTile t;
+        t.constraint = k;
+        t.start = (int)(u * VGX_REG_UNIT);
+        t.count = (int)std::min<int64_t>(take * VGX_REG_UNIT, (int64_t)cons[k].n - t.start);
+        tiles.push_back(t);
+        u += take;
+      }
+      ubase += uc;
+    }
+    while ((int)cta_tile_begin.size() <= g->n_ctas) cta_tile_begin.push_back((int)tiles.size());
   }
+  tile_begin.push_back((int)tiles.size());
   g->n_tiles = (int)tiles.size();
-  // persistent grid: all co-resident CTAs, but no more warps than tiles
-  {
-    const int warps_per_cta = VGX_REG_THREADS / 32;
-    const int want = (g->n_tiles + warps_per_cta - 1) / warps_per_cta;
-    g->n_ctas = std::max(0, std::min(vgx_reg_resident_ctas(c->device), want));
+  for (auto& t : tiles) {   // what the CTA needs to start its bulk copies without a dependent load
+    const RegConstraintDev& cc = cons[t.constraint];
+    const int cells = cc.gd0 * cc.gd1 * cc.gd2;
+    t.pts = cc.pts + (size_t)(t.start / VGX_REG_UNIT) * VGX_PT_UNIT_FLOATS;
+    t.grid16 = cc.grid16;
+    t.grid_bytes = (cc.grid16 && cells > 0) ? (int)((((size_t)cells + 7) & ~(size_t)7) * sizeof(uint16_t)) : 0;
   }
   g->n_rel_local = (c->rank == 0) ? (int)g->rel.size() : 0;
 
@@ -1143,6 +1184,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   if (e == cudaSuccess) e = upload_vec(&g->d_cons, cons, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tiles, tiles, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tile_begin, tile_begin, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_cta_tile_begin, cta_tile_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
@@ -1156,8 +1198,6 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_partials, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_tiles);
   dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
   dmalloc((void**)&g->d_counters, sizeof(int) * (size_t)g->n_local);
-  dmalloc((void**)&g->d_sched, sizeof(int) * 2);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_sched, 0, sizeof(int) * 2, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counters, 0, std::max<size_t>(sizeof(int) * (size_t)g->n_local, 4), st);
   // a constraint without points owns no tile: its sums must read as zero
   if (e == cudaSuccess) e = cudaMemsetAsync(g->d_csum, 0, std::max<size_t>(sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local, 8), st);
@@ -1193,21 +1233,27 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     {
       VgxLaunchScope s(c, 0);
-      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_tiles, g->n_ctas, g->d_tile_begin,
-                            g->d_counters, g->d_sched, g->d_partials, g->d_csum, jacobian);
+      vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_ctas, g->d_cta_tile_begin,
+                            g->d_tile_begin, g->d_counters, g->d_partials, g->d_csum, g->grid_capacity,
+                            jacobian);
     }
   }
-  // multi-rank: assemble straight into the NVLink-exported buffer when the peer path is up
-  double* d_asm = d_packed;
+  // multi-rank peer path: the assembly pushes this rank's partial into every rank's region
   const bool p2p = c->nranks > 1 && c->p2p_ready;
+  VgxP2PPush push;
   VgxP2PSignal sig;
+  VgxP2PGather gat;
+  memset(&push, 0, sizeof(push));
   memset(&sig, 0, sizeof(sig));
+  memset(&gat, 0, sizeof(gat));
+  push.n = 1;
+  push.dst[0] = d_packed;
   if (p2p) {
-    int rc = vgx_p2p_begin(c, g->packed_len, &d_asm, &sig);
+    int rc = vgx_p2p_begin(c, g->packed_len, &push, &sig, &gat);
     if (rc != VGX_OK) return rc;
   }
   if (p2p && c->p2p_fused && g->packed_len < (size_t)INT_MAX) {
-    // one launch: assemble -> signal -> wait -> gather-sum (grid fully co-resident)
+    // one launch: assemble + push -> signal -> wait -> local reduce (grid fully co-resident)
     static int resident = 0;
     if (resident == 0) {
       int sms = 0, per_sm = 0;
@@ -1216,16 +1262,11 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
         per_sm = 1;
       resident = std::max(1, sms * std::max(per_sm, 1));
     }
-    VgxP2PGather gat;
-    memset(&gat, 0, sizeof(gat));
-    const void* bufs[8];
-    vgx_p2p_gather_sources(c, bufs, &gat.timeout_flag);
-    for (int r = 0; r < c->nranks; ++r) gat.buf[r] = (const double*)bufs[r];
     const int grid = std::min(g->N + g->E + 1, std::min(resident, 592));
     {
       VgxLaunchScope s(c, 5);
       assemble_exchange_kernel<<<grid, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
-                                                    g->d_csr_items, d_asm, g->N, g->E, g->n_local,
+                                                    g->d_csr_items, push, g->N, g->E, g->n_local,
                                                     g->n_rel_local, do_reg ? 0 : 1, sig, gat, d_packed,
                                                     (int)g->packed_len);
     }
@@ -1235,11 +1276,11 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   {
     VgxLaunchScope s(c, 5);
     assemble_kernel<<<g->N + g->E + 1, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
-                                                     g->d_csr_items, d_asm, g->N, g->E, g->n_local,
+                                                     g->d_csr_items, push, g->N, g->E, g->n_local,
                                                      g->n_rel_local, do_reg ? 0 : 1, sig);
   }
   VGX_CUDA(c, cudaGetLastError());
-  if (p2p) return vgx_p2p_gather(c, d_packed, g->packed_len);
+  if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len);
   return vgx_nccl_allreduce_sum_f64(c, d_packed, g->packed_len);
 }
 

@@ -1,50 +1,31 @@
-// One-shot all-gather-reduce of the packed normal equations over NVLink peer memory (CUDA IPC).
-// See vgx_comm_p2p_export / vgx_comm_p2p_import in include/voxgraph_b200.h.
+// One-shot all-gather-reduce of the packed normal equations over NVLink peer memory (CUDA IPC):
+// PUSH variant.  See vgx_comm_p2p_export / vgx_comm_p2p_import in include/voxgraph_b200.h and the
+// protocol description in vgx_internal.h.
 //
-// Per evaluation (epoch e, parity e & 1):
-//   assemble_kernel      writes this rank's partial into its own exported buffer[parity]
-//   (its last CTA)       __threadfence_system(), then stores e into flag[rank] of EVERY rank's region
-//   p2p_gather_kernel    waits until all flags in its own region reach e, then sums the partials of
-//                        ranks 0..n-1 in rank order straight out of peer memory (ld.volatile, no L1)
-// Two buffers suffice: a rank can only signal epoch e+1 after its own gather of e has finished
-// (stream order), and nobody passes the gather of e+1 before everybody signalled e+1.
+// Two parities suffice: a rank can only push epoch e+2 after its own gather of e+1 has finished
+// (stream order), which needs every rank's flag e+1, which a rank sets only after its gather of e.
 #include <stdlib.h>
 #include <string.h>
 
 #include "vgx_internal.h"
 
 #define P2P_FLAG_BYTES 256
+#define P2P_MAX_RANKS 8
 
-struct P2PPeers {
-  double* buf[8];                 // buffer[parity] of every rank
-  unsigned long long* flags[8];   // flag array of every rank
-  int nranks, rank;
-};
-
+// separate-launch gather (VGX_P2P_FUSED=0): wait for the flags, add the local slots in rank order
 __global__ void __launch_bounds__(256)
-p2p_gather_kernel(P2PPeers P, unsigned long long epoch, double* __restrict__ out, size_t count,
-                  int* __restrict__ timeout_flag) {
+p2p_gather_kernel(VgxP2PGather G, double* __restrict__ out, size_t count) {
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
-    const volatile unsigned long long* mine = P.flags[P.rank];
-    const long long t0 = clock64();
-    int ok = 1;
-    for (int r = 0; r < P.nranks; ++r) {
-      while (mine[r] < epoch) {
-        if (clock64() - t0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer is gone
-      }
-      if (!ok) break;
-    }
+    s_ok = vgx_p2p_wait(G) ? 1 : 0;
     __threadfence_system();
-    s_ok = ok;
-    if (!ok) *timeout_flag = 1;
   }
   __syncthreads();
-  if (!s_ok) return;
+  const bool ok = s_ok != 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int r = 0; r < P.nranks; ++r) s += *((const volatile double*)(P.buf[r] + i));
-    out[i] = s;
+    for (int r = 0; r < G.nranks; ++r) s += *((const volatile double*)(G.slot[r] + i));
+    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // poison on timeout: LM sees an invalid step
   }
 }
 
@@ -66,7 +47,8 @@ extern "C" int vgx_comm_p2p_export(vgx_ctx* c, uint64_t capacity_doubles, uint8_
   VGX_CUDA(c, cudaSetDevice(c->device));
   vgx_p2p_free(c);
   const size_t cap = ((size_t)capacity_doubles + 31) & ~(size_t)31;
-  const size_t bytes = P2P_FLAG_BYTES + 2 * cap * sizeof(double);
+  // the rank count is not known yet: room for the 8 source ranks of one node, two parities
+  const size_t bytes = P2P_FLAG_BYTES + 2 * (size_t)P2P_MAX_RANKS * cap * sizeof(double);
   VGX_CUDA(c, cudaMalloc(&c->p2p_base, bytes));
   VGX_CUDA(c, cudaMemset(c->p2p_base, 0, bytes));
   cudaIpcMemHandle_t h;
@@ -78,7 +60,7 @@ extern "C" int vgx_comm_p2p_export(vgx_ctx* c, uint64_t capacity_doubles, uint8_
 }
 
 extern "C" int vgx_comm_p2p_import(vgx_ctx* c, int nranks, int rank, const uint8_t* handles) {
-  if (!c || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return VGX_ERR_INVALID;
+  if (!c || !handles || nranks < 1 || nranks > P2P_MAX_RANKS || rank < 0 || rank >= nranks) return VGX_ERR_INVALID;
   if (!c->p2p_base) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_comm_p2p_import: call vgx_comm_p2p_export first");
   if (c->nccl_comm && (c->nranks != nranks || c->rank != rank))
     VGX_FAIL(c, VGX_ERR_INVALID, "vgx_comm_p2p_import: rank layout differs from vgx_comm_init");
@@ -95,9 +77,17 @@ extern "C" int vgx_comm_p2p_import(vgx_ctx* c, int nranks, int rank, const uint8
   c->rank = rank;
   c->p2p_ready = true;
   {
-    // the one-launch path is opt-in until it has been validated on every rank count
+    // one launch (assemble + push + wait + reduce) by default; VGX_P2P_FUSED=0 selects two launches
     const char* f = getenv("VGX_P2P_FUSED");
-    c->p2p_fused = f && f[0] == '1';
+    c->p2p_fused = !(f && f[0] == '0');
+    // a rank that lags (first-launch module load, table builds, uploads) must not look dead:
+    // generous default, VGX_P2P_TIMEOUT_S overrides; callers barrier before the first exchange
+    const char* t = getenv("VGX_P2P_TIMEOUT_S");
+    double secs = t ? atof(t) : 30.0;
+    if (!(secs > 0)) secs = 30.0;
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    c->p2p_timeout_cycles = (long long)(secs * 1e3 * (double)khz);
   }
   vgx_graph_invalidate_registration(c);
   return VGX_OK;
@@ -106,49 +96,51 @@ extern "C" int vgx_comm_p2p_import(vgx_ctx* c, int nranks, int rank, const uint8
 int vgx_p2p_check(vgx_ctx* c) {
   if (!c->p2p_ready) return VGX_OK;
   int t = 0;
-  VGX_CUDA(c, cudaMemcpyAsync(&t, (char*)c->p2p_base + 128, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int* d_t = (int*)((char*)c->p2p_base + 128);
+  VGX_CUDA(c, cudaMemcpyAsync(&t, d_t, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VGX_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (t) VGX_FAIL(c, VGX_ERR_NCCL, "peer exchange timed out waiting for a rank (NVLink all-gather-reduce)");
+  if (t) {
+    VGX_CUDA(c, cudaMemsetAsync(d_t, 0, sizeof(int), c->stream));   // not sticky: the next call starts clean
+    VGX_FAIL(c, VGX_ERR_NCCL, "peer exchange timed out waiting for a rank (NVLink all-gather-reduce); "
+                              "the result of that evaluation is NaN");
+  }
   return VGX_OK;
 }
 
-int vgx_p2p_begin(vgx_ctx* c, size_t count, double** send_buf, VgxP2PSignal* sig) {
+static inline double* p2p_slot(void* region, size_t cap, unsigned long long epoch, int src_rank) {
+  return (double*)((char*)region + P2P_FLAG_BYTES) + ((epoch & 1) * P2P_MAX_RANKS + (size_t)src_rank) * cap;
+}
+
+int vgx_p2p_begin(vgx_ctx* c, size_t count, VgxP2PPush* push, VgxP2PSignal* sig, VgxP2PGather* gat) {
   if (!c->p2p_ready) VGX_FAIL(c, VGX_ERR_INVALID, "peer exchange not initialised");
   if (count > c->p2p_cap) VGX_FAIL(c, VGX_ERR_CAPACITY, "packed normal equations exceed the exported peer buffer");
   const unsigned long long e = ++c->p2p_epoch;
-  *send_buf = (double*)((char*)c->p2p_base + P2P_FLAG_BYTES) + (e & 1) * c->p2p_cap;
+  memset(push, 0, sizeof(*push));
   memset(sig, 0, sizeof(*sig));
+  memset(gat, 0, sizeof(*gat));
+  push->n = c->nranks;
   sig->epoch = e;
   sig->nranks = c->nranks;
   sig->rank = c->rank;
   sig->counter = (int*)((char*)c->p2p_base + 192);  // local word of the flag page
-  for (int r = 0; r < c->nranks; ++r) sig->flags[r] = (unsigned long long*)c->p2p_peer[r];
+  gat->flags = (const unsigned long long*)c->p2p_base;
+  gat->timeout_flag = (int*)((char*)c->p2p_base + 128);  // local word of the flag page, peers never touch it
+  gat->timeout_cycles = c->p2p_timeout_cycles;
+  gat->epoch = e;
+  gat->nranks = c->nranks;
+  for (int r = 0; r < c->nranks; ++r) {
+    push->dst[r] = p2p_slot(c->p2p_peer[r], c->p2p_cap, e, c->rank);   // my slot in rank r's region
+    sig->flags[r] = (unsigned long long*)c->p2p_peer[r];
+    gat->slot[r] = p2p_slot(c->p2p_base, c->p2p_cap, e, r);            // rank r's slot in my region
+  }
   return VGX_OK;
 }
 
-void vgx_p2p_gather_sources(vgx_ctx* c, const void* bufs[8], int** timeout_flag) {
-  const unsigned long long e = c->p2p_epoch;
-  for (int r = 0; r < 8; ++r)
-    bufs[r] = r < c->nranks ? (const void*)((double*)((char*)c->p2p_peer[r] + P2P_FLAG_BYTES) + (e & 1) * c->p2p_cap)
-                            : nullptr;
-  *timeout_flag = (int*)((char*)c->p2p_base + 128);
-}
-
-int vgx_p2p_gather(vgx_ctx* c, double* d_out, size_t count) {
-  const unsigned long long e = c->p2p_epoch;
-  P2PPeers P;
-  memset(&P, 0, sizeof(P));
-  P.nranks = c->nranks;
-  P.rank = c->rank;
-  for (int r = 0; r < c->nranks; ++r) {
-    P.flags[r] = (unsigned long long*)c->p2p_peer[r];
-    P.buf[r] = (double*)((char*)c->p2p_peer[r] + P2P_FLAG_BYTES) + (e & 1) * c->p2p_cap;
-  }
-  int* d_timeout = (int*)((char*)c->p2p_base + 128);  // local word of the flag page, peers never touch it
+int vgx_p2p_gather(vgx_ctx* c, const VgxP2PGather& gat, double* d_out, size_t count) {
   {
     VgxLaunchScope s(c, 5);
     const int blocks = (int)((count + 1023) / 1024) > 0 ? (int)((count + 1023) / 1024) : 1;
-    p2p_gather_kernel<<<blocks < 64 ? blocks : 64, 256, 0, c->stream>>>(P, e, d_out, count, d_timeout);
+    p2p_gather_kernel<<<blocks < 64 ? blocks : 64, 256, 0, c->stream>>>(gat, d_out, count);
   }
   VGX_CUDA(c, cudaGetLastError());
   return VGX_OK;

@@ -79,132 +79,107 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Registration reduce kernel, v6: warp-level dynamic scheduling.
-//
-// The residual index space of every constraint is cut into tiles of VGX_REG_TILE_UNITS 32-point
-// units (128 points).  The cost of a tile varies by 4x with the share of its points that land in
-// the reading submap (overlapping submaps share only part of their surface and consecutive
-// points are spatially coherent), so tiles are NOT pre-assigned: every warp of the persistent
-// grid draws tile tickets from a global counter and runs its own software pipeline, two tiles
-// deep, with no block-level synchronisation at all:
-//   * ticket t+2 is drawn and its points (TILE_UNITS x 640 contiguous bytes of the unit-major
-//     AoSoA layout) are requested with ONE cp.async.bulk (TMA 1-D) into the warp's 2-slot
-//     shared-memory ring, completing on an mbarrier, while tile t is processed;
-//   * per tile the constraint's descriptor + float pose block are staged in the warp's own
-//     shared-memory copy (lanes load one word each);
-//   * stage A(u+1): transform -> containing block -> block grid (global memory, L1/L2 resident,
-//     <= 16 KB per submap) -> base corner voxel -> the octet's two LDG.128 are ISSUED;
-//     stage B(u): the octet issued one unit earlier is consumed: B1 coefficients, residual,
-//     Jacobian, Gram staging + 8 DMMA.  Two register sets alternate so the in-flight octet is
-//     never copied.  A warp whose 32 points all miss the reading submap (getVoxelsAndQVector
-//     fails on its first block lookup) skips the unit after ~60 instructions;
-//   * the tile's 21 sums go to partials[tile]; the warp that finishes a constraint's last tile
-//     (atomic ticket) adds the constraint's partials in tile order -> bit-reproducible results
-//     whatever warp processed which tile.
-// The last unit of a constraint is zero-padded to 32 points (weight 0 -> zero contribution).
-#define VGX_REG_UNIT_FLOATS 160
-#define VGX_REG_TILE_BYTES (VGX_REG_TILE_UNITS * 640)
-
-struct RegPipeRegs {   // what stage A hands to stage B
-  float4 lo, hi;       // the octet (NaN when the block is missing)
-  float ox, oy, oz;
-  bool found;
-};
-
-// block grid of the reading submap in global memory (int32 slots, -1 = no block)
-__device__ __forceinline__ int vgx_grid_slot_g(const RegConstraintDev& C, int b0, int b1, int b2) {
-  const int g0 = b0 - C.gmin0, g1 = b1 - C.gmin1, g2 = b2 - C.gmin2;
-  const bool in = (unsigned)g0 < (unsigned)C.gd0 && (unsigned)g1 < (unsigned)C.gd1 &&
-                  (unsigned)g2 < (unsigned)C.gd2;
-  return in ? __ldg(C.grid + (g2 * C.gd1 + g1) * C.gd0 + g0) : -1;
-}
-
+// Registration reduce kernel, v4.  Persistent CTAs; the local residual index space is cut into
+// 32-point units that are dealt evenly to the CTAs (a tile = a CTA's run of units inside one
+// residual block).  Inside a tile every warp runs its own software pipeline over the units
+// u = warp, warp + W, ...:
+//   * the unit's points (640 contiguous bytes of the unit-major AoSoA layout) are brought into a
+//     per-warp 4-slot shared-memory ring by ONE cp.async.bulk (TMA 1-D) completing on an
+//     mbarrier, three units ahead - the point loads never touch the LSU path of the math warps;
+//   * stage A(u+1): transform -> voxel index -> block-grid lookup (shared memory) -> the octet's
+//     two LDG.128 are ISSUED;  stage B(u): the octet issued one iteration earlier is consumed:
+//     B1 coefficients, residual, Jacobian, Gram staging + 8 DMMA.  The gather latency of unit
+//     u+1 is hidden behind the arithmetic of unit u inside the same warp.
+// The last unit is zero-padded to 32 points (weight 0 -> zero contribution), so the
+// loop carries no "active" predicate.  Warps never synchronise with each other inside a tile.
 template <bool kJacobian>
 __global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
-                  int n_tiles, const int* __restrict__ tile_begin, int* __restrict__ counters,
-                  int* __restrict__ sched /* [0] next ticket, [1] warps that have left */,
-                  double* __restrict__ partials, double* __restrict__ csum) {
+                  const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_begin,
+                  int* __restrict__ counters, double* __restrict__ partials,
+                  double* __restrict__ csum, int grid_capacity) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
-  constexpr int kTU = VGX_REG_TILE_UNITS;
-  __shared__ __align__(128) float s_ring[kWarps][2][kTU * VGX_REG_UNIT_FLOATS];
-  __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
+  constexpr int kRing = VGX_REG_RING;
+  __shared__ __align__(128) float s_ring[kWarps][kRing][5][32];
+  __shared__ __align__(8) unsigned long long s_bar[kWarps][kRing];
+  __shared__ __align__(8) unsigned long long s_tbar;   // tile barrier: descriptor + pose block + grid
   __shared__ double s_stage[kWarps][6][VGX_STAGE_STRIDE];
   __shared__ double s_gram[kWarps][64];
-  __shared__ __align__(16) RegConstraintDev s_Cw[kWarps];
-  __shared__ __align__(16) RegPoseConst s_Pw[kWarps];
+  __shared__ __align__(16) RegConstraintDev s_C;
+  __shared__ __align__(16) RegPoseConst s_P;
+  __shared__ int s_last;
+  extern __shared__ __align__(16) uint16_t s_grid[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
-  const RegConstraintDev& C = s_Cw[warp];
   if (lane == 0) {
-    mbar_init(smem_u32(&s_bar[warp][0]), 1);
-    mbar_init(smem_u32(&s_bar[warp][1]), 1);
+#pragma unroll
+    for (int k = 0; k < kRing; ++k) mbar_init(smem_u32(&s_bar[warp][k]), 1);
+    if (warp == 0) mbar_init(smem_u32(&s_tbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
-  const uint32_t ring0 = smem_u32(&s_ring[warp][0][0]);
+  __syncthreads();
+  const uint32_t ring0 = smem_u32(&s_ring[warp][0][0][0]);
   const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
-  const float* ringf = &s_ring[warp][0][0] + lane;
+  const uint32_t tbar = smem_u32(&s_tbar);
+  const float* ringf = &s_ring[warp][0][0][0];
   double* stage_w = &s_stage[warp][0][lane];
   const double* stage_r = &s_stage[warp][grp < 6 ? grp : 0][tig];
+  uint32_t it = 0;   // units consumed by this warp so far: ring slot = it % kRing, parity = (it / kRing) & 1
+  int grid_of = -1;  // constraint whose block grid is currently staged
 
-  auto draw = [&]() -> int {  // next tile ticket, warp-uniform
-    int t = 0;
-    if (lane == 0) t = atomicAdd(sched, 1);
-    return __shfl_sync(0xffffffffu, t, 0);
-  };
-  // request tile t's points into ring slot `slot` (lane 0); returns the tile record to all lanes
-  auto request = [&](int t, uint32_t slot) -> RegTile {
+  uint32_t tseq = 0;  // tiles staged by this CTA (parity of the tile barrier)
+  for (int tile = cta_tile_begin[blockIdx.x]; tile < cta_tile_begin[blockIdx.x + 1]; ++tile, ++tseq) {
+    // the 32-byte tile record is all a thread needs to start the bulk copies
+    const int4 rec0 = __ldg(reinterpret_cast<const int4*>(tiles + tile));
+    const ulonglong2 rec1 = __ldg(reinterpret_cast<const ulonglong2*>(tiles + tile) + 1);
     RegTile T;
-    T.constraint = -1; T.start = 0; T.count = 0; T.pad = 0;
-    if (t < n_tiles) {
-      const int4 raw = __ldg(reinterpret_cast<const int4*>(tiles + t));
-      T.constraint = raw.x; T.start = raw.y; T.count = raw.z;
+    T.constraint = rec0.x; T.start = rec0.y; T.count = rec0.z; T.grid_bytes = rec0.w;
+    T.pts = reinterpret_cast<const float*>(rec1.x);
+    T.grid16 = reinterpret_cast<const uint16_t*>(rec1.y);
+    const bool use_grid = T.grid_bytes > 0 && T.grid_bytes <= 2 * grid_capacity;
+    const bool stage_grid = use_grid && grid_of != T.constraint;
+    __syncthreads();  // previous tile: every warp is out of its loop (s_C / s_P / s_grid readers)
+    // ---- descriptor (160 B), pose block (64 B) and the 16-bit block grid: three bulk copies on the
+    //      tile barrier; the warps' first point units follow on their own barriers
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)sizeof(RegConstraintDev) + (uint32_t)sizeof(RegPoseConst) +
+                             (stage_grid ? (uint32_t)T.grid_bytes : 0u);
+      mbar_expect_tx(tbar, bytes);
+      tma_load_1d(smem_u32(&s_C), constraints + T.constraint, (uint32_t)sizeof(RegConstraintDev), tbar);
+      tma_load_1d(smem_u32(&s_P), poses + T.constraint, (uint32_t)sizeof(RegPoseConst), tbar);
+      if (stage_grid) tma_load_1d(smem_u32(s_grid), T.grid16, (uint32_t)T.grid_bytes, tbar);
+    }
+    if (stage_grid) grid_of = T.constraint;
+    const int n_units = (T.count + 31) >> 5;
+    const int my_units = warp < n_units ? (n_units - warp + kWarps - 1) / kWarps : 0;
+    // producer (lane 0): bring unit j of this warp into ring slot seq % kRing
+    auto issue = [&](int j, uint32_t seq) {
       if (lane == 0) {
-        const float* src = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(
-                               &constraints[T.constraint].pts))) +
-                           (size_t)(T.start >> 5) * VGX_REG_UNIT_FLOATS;
-        const uint32_t bytes = 640u * (uint32_t)((T.count + 31) >> 5);
-        mbar_expect_tx(bar0 + 8u * slot, bytes);
-        tma_load_1d(ring0 + (uint32_t)VGX_REG_TILE_BYTES * slot, src, bytes, bar0 + 8u * slot);
+        const uint32_t slot = seq % kRing;
+        const uint32_t bar = bar0 + 8u * slot, dst = ring0 + 640u * slot;
+        mbar_expect_tx(bar, 640u);
+        tma_load_1d(dst, T.pts + (size_t)(warp + j * kWarps) * VGX_PT_UNIT_FLOATS, 640u, bar);
       }
+    };
+    if (my_units > 0) {
+#pragma unroll
+      for (int j = 0; j < kRing - 1; ++j)
+        if (j < my_units) issue(j, it + j);
     }
-    return T;
-  };
-
-  uint32_t seq = 0;  // tiles consumed by this warp: ring slot = seq & 1, barrier parity = (seq >> 1) & 1
-  int t_cur = draw();
-  RegTile T_cur = request(t_cur, 0);
-  int t_nxt = draw();
-  RegTile T_nxt = request(t_nxt, 1);
-
-  while (t_cur < n_tiles) {
-    const uint32_t slot = seq & 1u;
-    // ---- stage the constraint descriptor + pose block in the warp's shared-memory copy
-    {
-      constexpr int kWc = (int)(sizeof(RegConstraintDev) / 4), kWp = (int)(sizeof(RegPoseConst) / 4);
-      const uint32_t* gc = reinterpret_cast<const uint32_t*>(constraints + T_cur.constraint);
-      const uint32_t* gp = reinterpret_cast<const uint32_t*>(poses + T_cur.constraint);
-      uint32_t* sc = reinterpret_cast<uint32_t*>(&s_Cw[warp]);
-      uint32_t* sp = reinterpret_cast<uint32_t*>(&s_Pw[warp]);
-      for (int k = lane; k < kWc; k += 32) sc[k] = __ldg(gc + k);
-      if (lane < kWp) sp[lane] = __ldg(gp + lane);
-      __syncwarp();
-    }
-    const RegPoseConst P = s_Pw[warp];
-    const int n_units = (T_cur.count + 31) >> 5;
-    const bool use_grid = C.grid != nullptr;
-    const size_t vox_shift = 3 * C.vps_shift;
-    const float4* view = reinterpret_cast<const float4*>(C.view);
-    const bool gram_always = C.no_corr != 0.0;  // r = w * no_correspondence_cost without a match
-    const float* tile_ring = ringf + slot * (kTU * VGX_REG_UNIT_FLOATS);
+    mbar_wait(tbar, tseq & 1u);   // descriptor, pose block and grid have landed
+    const RegPoseConst P = s_P;
     double d0 = 0.0, d1 = 0.0;
-    mbar_wait(bar0 + 8u * slot, (seq >> 1) & 1u);  // this tile's points have landed
+    const size_t vox_shift = 3 * s_C.vps_shift;
+    const float4* view = reinterpret_cast<const float4*>(s_C.view);
 
-    // stage A: everything up to the ISSUE of the octet loads
-    auto stage_a = [&](int u, RegPipeRegs& R) {
-      const float* sp = tile_ring + u * VGX_REG_UNIT_FLOATS;
+    // stage A: everything up to the ISSUE of the octet load
+    struct Pipe { float4 lo, hi; float ox, oy, oz; bool found; };
+    const bool gram_always = s_C.no_corr != 0.0;  // r = w * no_correspondence_cost without a match
+    auto stage_a = [&](uint32_t seq, Pipe& R) {
+      const uint32_t slot = seq % kRing;
+      mbar_wait(bar0 + 8u * slot, (seq / kRing) & 1u);
+      const float* sp = ringf + 160 * slot + lane;
       float p0, p1, p2;
       vgx_reg_transform(P, sp[0], sp[32], sp[64], p0, p1, p2);
       const float qnan = __int_as_float(0x7fc00000);
@@ -213,39 +188,56 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       R.found = false;
       R.ox = R.oy = R.oz = 0.f;
       int b0, b1, b2;
-      vgx_block_index(C, p0, p1, p2, b0, b1, b2);
+      vgx_block_index(s_C, p0, p1, p2, b0, b1, b2);
       RegLocate L;
       int slot_b;
       if (use_grid) {
-        // getVoxelsAndQVector fails right away when the block that contains pos does not exist
-        const bool hit = vgx_grid_slot_g(C, b0, b1, b2) >= 0;
+#if VGX_REG_EARLYOUT
+        // getVoxelsAndQVector fails right away when the block that contains pos does not exist;
+        // overlapping submaps share only part of their surface and consecutive points are
+        // spatially coherent: most warps miss with all 32 lanes and skip the rest of the unit
+        const bool hit = vgx_grid_slot(s_C, s_grid, b0, b1, b2) >= 0;
         if (!__any_sync(0xffffffffu, hit)) return;
-        vgx_locate_in_block<false>(C, p0, p1, p2, b0, b1, b2, L, nullptr, true);
-        slot_b = hit ? vgx_grid_slot_g(C, L.b0, L.b1, L.b2) : -1;
+        vgx_locate_in_block<true>(s_C, p0, p1, p2, b0, b1, b2, L, s_grid);
+        slot_b = hit ? L.slot : -1;
+#else
+        vgx_locate_in_block<true>(s_C, p0, p1, p2, b0, b1, b2, L, s_grid);
+        slot_b = L.slot;
+#endif
       } else {
-        vgx_locate_in_block<false>(C, p0, p1, p2, b0, b1, b2, L);
-        slot_b = vgx_resolve(C, L);
+        vgx_locate_in_block<false>(s_C, p0, p1, p2, b0, b1, b2, L);
+        slot_b = vgx_resolve(s_C, L);
       }
       R.found = slot_b >= 0;
       R.ox = L.ox; R.oy = L.oy; R.oz = L.oz;
       if (R.found) {
         const float4* o = view + 2 * (((size_t)slot_b << vox_shift) + (size_t)L.lin);
-#if VGX_REG_STREAM_OCTETS
-        R.lo = __ldcs(o); R.hi = __ldcs(o + 1);
+#if VGX_REG_LDG256
+        // the whole 32-byte octet = one sector = ONE 256-bit load (SASS LDG.E.ENL2.256)
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(R.lo.x), "=f"(R.lo.y), "=f"(R.lo.z), "=f"(R.lo.w), "=f"(R.hi.x), "=f"(R.hi.y),
+                       "=f"(R.hi.z), "=f"(R.hi.w)
+                     : "l"(o));
 #else
         R.lo = __ldg(o); R.hi = __ldg(o + 1);
 #endif
       }
     };
     // stage B: consume the octet issued one unit ago
-    auto stage_b = [&](int u, const RegPipeRegs& R) {
-      const float* sp = tile_ring + u * VGX_REG_UNIT_FLOATS;
+    auto stage_b = [&](uint32_t seq, const Pipe& R) {
+      const float* sp = ringf + 160 * (seq % kRing) + lane;
       const float d[8] = {R.lo.x, R.lo.y, R.lo.z, R.lo.w, R.hi.x, R.hi.y, R.hi.z, R.hi.w};
+#if VGX_REG_SKIPGRAM
       bool ok = false;
       if (__any_sync(0xffffffffu, R.found)) ok = R.found && vgx_octet_ok(d);
-      if (gram_always || __any_sync(0xffffffffu, ok)) {
+      const bool work = gram_always || __any_sync(0xffffffffu, ok);
+#else
+      const bool ok = R.found && vgx_octet_ok(d);
+      const bool work = true;
+#endif
+      if (work) {
         const float xi = sp[0], yi = sp[32], dist = sp[96], w = sp[128];
-        const RegPointResult Q = vgx_reg_math<kJacobian>(C, P, xi, yi, dist, w, ok, d, R.ox, R.oy, R.oz);
+        const RegPointResult Q = vgx_reg_math<kJacobian>(s_C, P, xi, yi, dist, w, ok, d, R.ox, R.oy, R.oz);
         if (kJacobian) {
           stage_w[0 * VGX_STAGE_STRIDE] = (double)Q.jr[0];
           stage_w[1 * VGX_STAGE_STRIDE] = (double)Q.jr[1];
@@ -259,45 +251,46 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
             const double a = (grp < 6) ? stage_r[4 * t4] : 0.0;
             dmma_8x8x4(d0, d1, a, a);
           }
-          __syncwarp();
         } else {
           d0 = fma(Q.r, Q.r, d0);
         }
       }
+      __syncwarp();  // every lane is done with this unit's ring slot and the Gram staging buffer
     };
 
-    {
-      RegPipeRegs Ra, Rb;
-      stage_a(0, Ra);
-      int u = 0;
-      for (; u + 2 <= n_units; u += 2) {
-        stage_a(u + 1, Rb);
-        stage_b(u, Ra);
-        if (u + 2 < n_units) stage_a(u + 2, Ra);
-        stage_b(u + 1, Rb);
+    if (my_units > 0) {
+      // two register sets alternate (loop unrolled by two): the in-flight octet is never copied
+      Pipe Ra, Rb;
+      stage_a(it, Ra);
+      int j = 0;
+      for (; j + 2 <= my_units; j += 2, it += 2) {
+        if (j + kRing - 1 < my_units) issue(j + kRing - 1, it + kRing - 1);
+        stage_a(it + 1, Rb);
+        stage_b(it, Ra);
+        if (j + kRing < my_units) issue(j + kRing, it + kRing);
+        if (j + 2 < my_units) stage_a(it + 2, Ra);
+        stage_b(it + 1, Rb);
       }
-      if (u < n_units) stage_b(u, Ra);
+      if (j < my_units) {
+        stage_b(it, Ra);
+        ++it;
+      }
     }
-    __syncwarp();  // every lane is done with the ring slot and the constants
-    // ---- the slot is free: draw the ticket after next and request its points
-    const int t_new = draw();
-    const RegTile T_new = request(t_new, slot);
-
-    // ---- tile epilogue: warp Gram fragment -> 21 sums -> partials[tile]
+    // ---- tile epilogue: warp Gram fragments -> 21 sums -> partials[tile]
     if (kJacobian) {
       s_gram[warp][grp * 8 + 2 * tig] = d0;
       s_gram[warp][grp * 8 + 2 * tig + 1] = d1;
     } else {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, off);
+      if (lane == 0) s_gram[warp][0] = d0;
     }
-    __syncwarp();
-    const int cidx = T_cur.constraint;
-    const double factor = C.factor;
-    if (lane < VGX_REG_NSUM) {
+    __syncthreads();
+    const double factor = s_C.factor;
+    if (threadIdx.x < VGX_REG_NSUM) {
       // entry e of the 21 sums -> (row, col) of the Gram matrix
       int row = 5, col = 5;
-      const int e = lane;
+      const int e = threadIdx.x;
       if (e < 15) {
         int p = 0, rem = e;
         while (rem >= 5 - p) { rem -= 5 - p; ++p; }
@@ -305,40 +298,40 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       } else if (e < 20) {
         row = e - 15; col = 5;
       }
-      double sv = 0;
-      if (kJacobian) sv = s_gram[warp][row * 8 + col];
-      else if (e == 20) sv = d0;
-      partials[(size_t)t_cur * VGX_REG_NSTRIDE + e] = sv;
-      __threadfence();
-    }
-    __syncwarp();
-    // the warp that completes the constraint adds its partials in tile order (cpp:274-291: factor^2)
-    const int t0 = tile_begin[cidx], t1 = tile_begin[cidx + 1];
-    int last = 0;
-    if (lane == 0) last = (atomicAdd(counters + cidx, 1) == t1 - t0 - 1);
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      if (lane < VGX_REG_NSUM) {
-        double sv = 0;
-        for (int t = t0; t < t1; ++t) sv += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + lane);
-        csum[(size_t)cidx * VGX_REG_NSTRIDE + lane] = sv * (factor * factor);
+      double s = 0;
+      if (kJacobian) {
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][row * 8 + col];
+      } else if (e == 20) {
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
       }
-      if (lane == 0) counters[cidx] = 0;
+      partials[(size_t)tile * VGX_REG_NSTRIDE + e] = s;
     }
-    __syncwarp();
-    t_cur = t_nxt; T_cur = T_nxt;
-    t_nxt = t_new; T_nxt = T_new;
-    ++seq;
-  }
-  // ---- the last warp to leave re-arms the scheduler for the next launch
-  if (lane == 0) {
-    const int total = (int)(gridDim.x * kWarps);
-    __threadfence();
-    if (atomicAdd(sched + 1, 1) == total - 1) {
-      sched[0] = 0;
-      sched[1] = 0;
+    // The last tile of a constraint to finish sums the constraint's partials in tile order
+    // (bit-reproducible) and applies factor^2 (cpp:274-291).
+    const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
+    if (t1 - t0 == 1) {
+      if (threadIdx.x < VGX_REG_NSUM)  // single tile: no ticket needed (same thread wrote the partial)
+        csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] =
+            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (factor * factor);
+    } else {
       __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int done = atomicAdd(counters + T.constraint, 1);
+        s_last = (done == t1 - t0 - 1);
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (threadIdx.x < VGX_REG_NSUM) {
+          double s = 0;
+          for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
+          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (factor * factor);
+        }
+        if (threadIdx.x == 0) counters[T.constraint] = 0;
+      }
     }
   }
 }
@@ -361,22 +354,27 @@ void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, co
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, int n_ctas, const int* tile_begin,
-                           int* counters, int* sched, double* partials, double* csum, bool jacobian) {
-  if (n_ctas <= 0 || n_tiles <= 0) return;
+                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
+                           const int* tile_begin, int* counters, double* partials, double* csum,
+                           int grid_capacity, bool jacobian) {
+  if (n_ctas <= 0) return;
+  const size_t smem = sizeof(uint16_t) * (size_t)grid_capacity;
   if (jacobian)
-    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, n_tiles, tile_begin,
-                                                               counters, sched, partials, csum);
+    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
+                                                                  tile_begin, counters, partials, csum,
+                                                                  grid_capacity);
   else
-    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, 0, st>>>(cons, poses, tiles, n_tiles, tile_begin,
-                                                                counters, sched, partials, csum);
+    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
+                                                                   tile_begin, counters, partials, csum,
+                                                                   grid_capacity);
 }
 
-int vgx_reg_resident_ctas(int device) {
+int vgx_reg_resident_ctas(int device, int grid_capacity) {
   int sms = 148, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t smem = sizeof(uint16_t) * (size_t)grid_capacity;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_reduce_kernel<true>, VGX_REG_THREADS,
-                                                    0) != cudaSuccess || per_sm <= 0)
+                                                    smem) != cudaSuccess || per_sm <= 0)
     per_sm = VGX_REG_MIN_BLOCKS;
   static const char* env = getenv("VGX_REG_CTAS_PER_SM");  // tuning override
   if (env && atoi(env) > 0) per_sm = atoi(env);
@@ -423,6 +421,9 @@ int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx
   if (!ref || !rd) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "registration constraint: unknown submap");
   if (!rd->finished || !rd->d_view)
     VGX_FAIL(c, VGX_ERR_INVALID, "registration constraint: reading submap is not finished");
+  if (cfg->use_esdf_distance && !rd->d_view_esdf)
+    VGX_FAIL(c, VGX_ERR_INVALID, "registration constraint: use_esdf_distance needs the reading submap's ESDF "
+                                 "(vgx_submap_generate_esdf)");
   const VgxPoints& p = ref->points[cfg->registration_point_type];
   const bool is_sampled = cfg->sampling_ratio != -1.0f;
   RegConstraintDev C;
@@ -430,11 +431,12 @@ int vgx_fill_constraint(vgx_ctx* c, uint32_t ref_id, uint32_t read_id, const vgx
   C.n = reg_num_residuals(p, cfg);
   C.ref_node = -1; C.read_node = -1;
   C.hash = rd->hash;
-  C.view = rd->d_view;
+  C.view = cfg->use_esdf_distance ? rd->d_view_esdf : rd->d_view;   // cpp:133-153
   C.voxel_size = rd->voxel_size; C.voxel_size_inv = rd->voxel_size_inv;
   C.block_size = rd->block_size; C.block_size_inv = rd->block_size_inv;
   C.vps = rd->vps;
   C.grid = rd->d_grid;
+  C.grid16 = rd->d_grid16;
   C.gmin0 = rd->grid_min[0]; C.gmin1 = rd->grid_min[1]; C.gmin2 = rd->grid_min[2];
   C.gd0 = rd->grid_dim[0]; C.gd1 = rd->grid_dim[1]; C.gd2 = rd->grid_dim[2];
   C.vps_shift = 0;
@@ -454,6 +456,7 @@ extern "C" void vgx_reg_config_default(vgx_reg_config* cfg) {
   cfg->registration_point_type = VGX_POINTS_ISOSURFACE;  // h:20-21
   cfg->no_correspondence_cost = 0.0;                      // h:32
   cfg->sampling_ratio = -1.0f;                            // h:28
+  cfg->use_esdf_distance = 0;                             // h:35 defaults to true; needs an ESDF
 }
 
 extern "C" int vgx_reg_num_residuals(vgx_ctx* c, uint32_t ref_id, const vgx_reg_config* cfg, int* n) {

@@ -15,7 +15,7 @@
 #define VGX_COORD_EPS 1e-6f
 
 // Per-constraint, per-evaluation pose block (cpp:61-110).
-struct RegPoseConst {
+struct __align__(16) RegPoseConst {   // 64 bytes: staged by one cp.async.bulk
   float qw, qz;                          // T_reading__reference rotation (yaw-only quaternion)
   float tx, ty, tz;                      // T_reading__reference translation
   float cos_e, sin_e, cos_emo, sin_emo;  // cpp:91-96
@@ -23,7 +23,7 @@ struct RegPoseConst {
 };
 
 // Reading-submap view + reference points of one residual block.
-struct RegConstraintDev {
+struct __align__(16) RegConstraintDev {   // 160 bytes: staged by one cp.async.bulk
   const float* pts;    // reference registration points, unit-major AoSoA (vgx_internal.h VgxPoints)
   int n;
   int ref_node, read_node;
@@ -32,6 +32,7 @@ struct RegConstraintDev {
   float voxel_size, voxel_size_inv, block_size, block_size_inv;
   int vps, vps_shift;
   const int32_t* grid;  // dense block index over the reading submap's block AABB (or null)
+  const uint16_t* grid16;  // the same as 16-bit slots (0xFFFF = no block), padded to 16 bytes: TMA source
   int gmin0, gmin1, gmin2, gd0, gd1, gd2;
   double factor;       // num_residuals / summed_reference_weight (cpp:274)
   double no_corr;      // config.no_correspondence_cost
@@ -309,6 +310,62 @@ __device__ __forceinline__ RegPointResult vgx_reg_math(const RegConstraintDev& C
     R.je3 = m0 * ae03 + m1 * ae13;
   }
   return R;
+}
+
+// Branch-free form of vgx_reg_math for the fused reduce kernel: everything is computed, the
+// "interpolation impossible" case is selected at the end (NaN octets just flow through), so two
+// points per lane can be scheduled as two independent instruction streams.  Same operations in
+// the same order as vgx_reg_math -> identical values.
+__device__ __forceinline__ void vgx_reg_math_nb(const RegConstraintDev& C, const RegPoseConst& P,
+                                                float xi, float yi, float dist, float w, bool ok,
+                                                const float4& lo, const float4& hi, float ox, float oy,
+                                                float oz, double& r_out, float jr[4], float& je3) {
+  const float d0 = lo.x, d1 = lo.y, d2 = lo.z, d3 = lo.w, d4 = hi.x, d5 = hi.y, d6 = hi.z, d7 = hi.w;
+  const float a0 = d0;
+  const float a1 = -d0 + d4;
+  const float a2 = -d0 + d2;
+  const float a3 = -d0 + d1;
+  const float a4 = d0 - d2 - d4 + d6;
+  const float a5 = d0 - d1 - d2 + d3;
+  const float a6 = d0 - d1 - d4 + d5;
+  const float a7 = -d0 + d1 + d2 - d3 + d4 - d5 - d6 + d7;
+  const float q4 = ox * oy, q5 = oy * oz, q6 = oz * ox, q7 = ox * oy * oz;
+  float interp = 1.0f * a0;
+  interp = interp + ox * a1;
+  interp = interp + oy * a2;
+  interp = interp + oz * a3;
+  interp = interp + q4 * a4;
+  interp = interp + q5 * a5;
+  interp = interp + q6 * a6;
+  interp = interp + q7 * a7;
+  const double r = ((double)dist - (double)interp) * (double)w;  // cpp:158-163
+  const float finv = C.voxel_size_inv;
+  const float iDx = finv * ox, iDy = finv * oy, iDz = finv * oz;
+  const double inv = (double)finv;
+  const double Dx = (double)ox, Dy = (double)oy, Dz = (double)oz;
+  const double iDyd = inv * Dy, iDxd = inv * Dx;
+  const float iDyDz = (float)(iDyd * Dz), iDxDz = (float)(iDxd * Dz), iDxDy = (float)(iDxd * Dy);
+  float g0 = a1 * finv;
+  g0 = g0 + a4 * iDy; g0 = g0 + a6 * iDz; g0 = g0 + a7 * iDyDz;
+  float g1 = a2 * finv;
+  g1 = g1 + a4 * iDx; g1 = g1 + a5 * iDz; g1 = g1 + a7 * iDxDz;
+  float g2 = a3 * finv;
+  g2 = g2 + a5 * iDy; g2 = g2 + a6 * iDx; g2 = g2 + a7 * iDxDy;
+  const float ar03 = xi * P.sin_emo - yi * P.cos_emo;
+  const float ar13 = xi * P.cos_emo + yi * P.sin_emo;
+  const float ae03 = -xi * P.sin_emo + yi * P.cos_emo + P.dxs - P.dyc;
+  const float ae13 = -xi * P.cos_emo - yi * P.sin_emo + P.dxc + P.dys;
+  const float m0 = -w * g0, m1 = -w * g1, m2 = -w * g2;
+  const float j0 = m0 * P.cos_e + m1 * (-P.sin_e);
+  const float j1 = m0 * P.sin_e + m1 * P.cos_e;
+  const float j3 = m0 * ar03 + m1 * ar13;
+  const float j4 = m0 * ae03 + m1 * ae13;
+  r_out = ok ? r : (double)w * C.no_corr;  // cpp:164-166
+  jr[0] = ok ? j0 : 0.f;
+  jr[1] = ok ? j1 : 0.f;
+  jr[2] = ok ? m2 : 0.f;
+  jr[3] = ok ? j3 : 0.f;
+  je3 = ok ? j4 : 0.f;
 }
 
 // cpp:128-129  reading_coordinate = T_reading__reference * reference_coordinate

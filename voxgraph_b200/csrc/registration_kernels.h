@@ -12,8 +12,20 @@ struct RegPoseConst;
 #ifndef VGX_REG_MIN_BLOCKS
 #define VGX_REG_MIN_BLOCKS 5       // resident CTAs per SM the register budget is sized for
 #endif
-#ifndef VGX_REG_TILE_UNITS
-#define VGX_REG_TILE_UNITS 4       // units (x 32 points, x 640 B) per tile = per ticket = per TMA bulk copy
+#ifndef VGX_REG_RING
+#define VGX_REG_RING 4             // point-slice ring slots per warp (units in flight = RING - 1)
+#endif
+#ifndef VGX_REG_LDG256
+#define VGX_REG_LDG256 1           // one 256-bit load per octet (LDG.E.ENL2.256) instead of two 128-bit ones
+#endif
+#ifndef VGX_REG_EARLYOUT
+#define VGX_REG_EARLYOUT 1         // a warp whose 32 points all miss the containing block skips the unit
+#endif
+#ifndef VGX_REG_SKIPGRAM
+#define VGX_REG_SKIPGRAM 1         // no Gram stage for a unit without a single correspondence
+#endif
+#ifndef VGX_REG_HW_TILE_UNITS
+#define VGX_REG_HW_TILE_UNITS 0    // > 0: one CTA per tile of that many units (hardware scheduling); 0: persistent
 #endif
 #define VGX_REG_UNIT 32            // points per unit = one warp iteration; tiles are cut on unit boundaries
 #ifndef VGX_REG_STREAM_OCTETS
@@ -22,22 +34,25 @@ struct RegPoseConst;
 #define VGX_REG_NSUM 21            // 15 (upper 5x5) + 5 (gradient) + 1 (cost)
 #define VGX_REG_NSTRIDE 24
 
-struct RegTile {
+struct __align__(16) RegTile {   // 32 bytes: everything a CTA needs to start its bulk copies
   int constraint;
   int start;
   int count;
-  int pad;
+  int grid_bytes;            // bytes of the 16-bit block grid to stage (multiple of 16), 0: hash path
+  const float* pts;          // first unit of the tile (unit-major points)
+  const uint16_t* grid16;
 };
 
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n);
-// Persistent warps draw tile tickets -> partial sums -> (last tile of each constraint)
-// per-constraint sums csum[c][21].  sched: 2 ints, zero before the first launch (the kernel re-arms it).
+// Persistent CTAs walk their tiles -> partial sums -> (last tile of each constraint)
+// per-constraint sums csum[c][21].
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
-                           const RegTile* tiles, int n_tiles, int n_ctas, const int* tile_begin,
-                           int* counters, int* sched, double* partials, double* csum, bool jacobian);
-// persistent grid size: SMs x co-resident CTAs
-int vgx_reg_resident_ctas(int device);
+                           const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
+                           const int* tile_begin, int* counters, double* partials, double* csum,
+                           int grid_capacity, bool jacobian);
+// persistent grid size: SMs x CTAs that are co-resident with `grid_capacity` cells of dynamic smem
+int vgx_reg_resident_ctas(int device, int grid_capacity);
 // Fills the descriptor of one (reference -> reading) residual block.  Deterministic mode: pts / n /
 // factor describe all registration points.  Sampling mode (*sampled = true): n = int(ratio * K),
 // factor = 1 (all weights forced to 1) and pts is left null for the caller, who draws the

@@ -84,8 +84,11 @@ static void free_submap(VgxSubmap* s) {
   cudaFree(s->d_block_idx);
   cudaFree(s->d_dw);
   cudaFree(s->d_view);
+  cudaFree(s->d_esdf);
+  cudaFree(s->d_view_esdf);
   cudaFree(s->d_counters);
   cudaFree(s->d_grid);
+  cudaFree(s->d_grid16);
   cudaFree(s->d_iso_idx);
   free_points(s->points[0]);
   free_points(s->points[1]);
@@ -229,7 +232,9 @@ __global__ void deinterleave_kernel(const float2* __restrict__ dw, float* __rest
 #define VGX_GRID_MAX_CELLS 4096
 int vgx_submap_build_grid(vgx_ctx* c, VgxSubmap* s) {
   cudaFree(s->d_grid);
+  cudaFree(s->d_grid16);
   s->d_grid = nullptr;
+  s->d_grid16 = nullptr;
   s->grid_dim[0] = s->grid_dim[1] = s->grid_dim[2] = 0;
   const int n = s->n_blocks;
   if (n <= 0) return VGX_OK;
@@ -253,8 +258,35 @@ int vgx_submap_build_grid(vgx_ctx* c, VgxSubmap* s) {
          (idx[3 * i] - lo[0])] = i;
   VGX_CUDA(c, cudaMalloc(&s->d_grid, sizeof(int32_t) * cells));
   VGX_CUDA(c, cudaMemcpyAsync(s->d_grid, grid.data(), sizeof(int32_t) * cells, cudaMemcpyHostToDevice, c->stream));
+  // 16-bit copy for the registration kernel's shared-memory grid (one bulk copy per tile)
+  std::vector<uint16_t> g16(((size_t)cells + 7) & ~(size_t)7, 0xFFFF);
+  for (long long k = 0; k < cells; ++k) g16[(size_t)k] = grid[(size_t)k] < 0 ? 0xFFFF : (uint16_t)grid[(size_t)k];
+  VGX_CUDA(c, cudaMalloc(&s->d_grid16, sizeof(uint16_t) * g16.size()));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_grid16, g16.data(), sizeof(uint16_t) * g16.size(), cudaMemcpyHostToDevice, c->stream));
   VGX_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int a = 0; a < 3; ++a) { s->grid_min[a] = lo[a]; s->grid_dim[a] = hi[a] - lo[a] + 1; }
+  return VGX_OK;
+}
+
+int vgx_submap_build_view(vgx_ctx* c, VgxSubmap* s, const float2* bricks, float* view) {
+  const size_t used = (size_t)s->n_blocks * s->vox_per_block;
+  if (used == 0) return VGX_OK;
+  int sh = 0;
+  while ((1 << sh) < s->vps) sh++;
+  build_view_kernel<<<(unsigned)((used + 255) / 256), 256, 0, c->stream>>>(bricks, s->d_block_idx, s->hash, view,
+                                                                          s->n_blocks, s->vps, sh);
+  c->launches++;
+  VGX_CUDA(c, cudaGetLastError());
+  return VGX_OK;
+}
+
+int vgx_submap_rebuild_hash(vgx_ctx* c, VgxSubmap* s) {
+  const uint32_t tsize = s->hash.mask + 1;
+  hash_clear_kernel<<<(tsize + 255) / 256, 256, 0, c->stream>>>(s->hash.entries, tsize);
+  if (s->n_blocks > 0)
+    hash_insert_kernel<<<(s->n_blocks + 127) / 128, 128, 0, c->stream>>>(s->hash, s->d_block_idx, s->n_blocks);
+  c->launches += 2;
+  VGX_CUDA(c, cudaGetLastError());
   return VGX_OK;
 }
 

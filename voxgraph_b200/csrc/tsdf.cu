@@ -5,13 +5,16 @@
 // (voxgraph/src/frontend/measurement_processors/pointcloud_integrator.cpp:66-84).
 // Compiled with -fmad=false (the float expressions are restated operation by operation).
 //
-// Two passes per scan, one thread per ray, both walking the identical DDA:
-//   1. allocate: insert every block a ray touches into the block hash (atomicCAS on the
-//      key, slot from an atomic counter) - replaces allocateStorageAndGetVoxelPtr +
-//      updateLayerWithStoredBlocks;
-//   2. integrate: per visited voxel a lock-free 64-bit CAS read-modify-write of the
-//      interleaved (distance, weight) pair - replaces the per-voxel mutex.
-// The order in which rays hit a voxel is unspecified (as in the multi-threaded reference).
+// mode 0 (Simple scheduling, every ray, every voxel) is RAY ORDERED: bit-identical to the
+//   single-threaded reference.  allocate pass (blocks of whole rays) -> per-ray update counts ->
+//   scan -> emit (voxel address, sdf, update weight) at the ray's offset -> stable radix sort by
+//   voxel address -> one thread (short segments) or one warp (long ones) applies a voxel's
+//   updates in ray order.
+// mode 1 (FastTsdfIntegrator scheduling, what voxgraph runs): one kernel, one thread per ray;
+//   blocks are allocated ON DEMAND for the voxels that are actually updated (as
+//   allocateStorageAndGetVoxelPtr does), the update is a lock-free 64-bit CAS read-modify-write of
+//   the interleaved (distance, weight) pair (replaces the per-voxel mutex); the order in which
+//   rays hit a voxel is unspecified, as in the multi-threaded reference.
 #include <math.h>
 #include <string.h>
 
@@ -158,6 +161,57 @@ __device__ __forceinline__ bool fast_start_ok(const TsdfParams& P, const float p
   return old != h;
 }
 
+// Block lookup with on-demand allocation (allocateStorageAndGetVoxelPtr): returns the brick slot,
+// or -1 when the submap's capacity is exhausted (counters[1] is raised; the key stays behind with
+// val = -2 until the host rebuilds the table).  Probe and wait loops are bounded: a full table or
+// a lost publisher ends in the overflow flag, never in a hang.
+template <bool kWait>
+__device__ __forceinline__ int tsdf_get_or_alloc(const VgxHash& hash, int32_t* __restrict__ block_idx,
+                                                 int* __restrict__ counters, int capacity, int b0,
+                                                 int b1, int b2) {
+  const uint64_t key = vgx_pack_key(b0, b1, b2);
+  uint32_t h = vgx_hash_index(b0, b1, b2, hash.mask);
+  for (uint32_t probes = 0; probes <= hash.mask; ++probes) {
+    uint64_t k = *((volatile uint64_t*)&hash.entries[h].key);
+    if (k == VGX_EMPTY_KEY) {
+      const unsigned long long prev = atomicCAS((unsigned long long*)&hash.entries[h].key,
+                                                (unsigned long long)VGX_EMPTY_KEY, (unsigned long long)key);
+      if (prev == VGX_EMPTY_KEY) {
+        const int slot = atomicAdd(counters, 1);
+        if (slot < capacity) {
+          block_idx[3 * slot] = b0; block_idx[3 * slot + 1] = b1; block_idx[3 * slot + 2] = b2;
+          __threadfence();
+          *((volatile int*)&hash.entries[h].val) = slot;
+          return slot;
+        }
+        counters[1] = 1;
+        *((volatile int*)&hash.entries[h].val) = -2;
+        return -1;
+      }
+      k = prev;
+    }
+    if (k == key) {
+      if (!kWait) return -1;  // insert-only pass: the slot is not needed yet
+      // another thread owns the insertion: wait until it publishes the slot.  The owner may be a
+      // lane of this very warp on a divergent path: __nanosleep suspends this lane so the
+      // scheduler runs the owner (plain spinning can starve it).
+      unsigned ns = 8;
+      for (int spin = 0; spin < (1 << 20); ++spin) {
+        const int v = *((volatile int*)&hash.entries[h].val);
+        if (v >= 0) return v;
+        if (v == -2) return -1;
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+      }
+      counters[1] = 1;
+      return -1;
+    }
+    h = (h + 1) & hash.mask;
+  }
+  counters[1] = 1;
+  return -1;
+}
+
 // ------------------------------------------------------------------ pass 1: allocate
 __global__ void __launch_bounds__(128)
 tsdf_allocate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
@@ -174,29 +228,7 @@ tsdf_allocate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
               b2 = (int)(g[2] >> P.vps_shift);
     if (b0 == lb0 && b1 == lb1 && b2 == lb2) continue;
     lb0 = b0; lb1 = b1; lb2 = b2;
-    const uint64_t key = vgx_pack_key(b0, b1, b2);
-    uint32_t h = vgx_hash_index(b0, b1, b2, hash.mask);
-    for (;;) {
-      const uint64_t k = *((volatile uint64_t*)&hash.entries[h].key);
-      if (k == key) break;
-      if (k == VGX_EMPTY_KEY) {
-        const unsigned long long prev = atomicCAS((unsigned long long*)&hash.entries[h].key,
-                                                  (unsigned long long)VGX_EMPTY_KEY,
-                                                  (unsigned long long)key);
-        if (prev == VGX_EMPTY_KEY) {
-          const int slot = atomicAdd(counters, 1);
-          if (slot < capacity) {
-            block_idx[3 * slot] = b0; block_idx[3 * slot + 1] = b1; block_idx[3 * slot + 2] = b2;
-            hash.entries[h].val = slot;
-          } else {
-            counters[1] = 1;  // overflow: block stays unmapped (vals == -1)
-          }
-          break;
-        }
-        if (prev == key) break;
-      }
-      h = (h + 1) & hash.mask;
-    }
+    tsdf_get_or_alloc<false>(hash, block_idx, counters, capacity, b0, b1, b2);
   }
 }
 
@@ -351,16 +383,32 @@ tsdf_apply_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ 
 
 // One warp per long segment: lanes fetch 32 consecutive tuples (coalesced), then every lane
 // replays them in order through shuffles, so the serial chain is pure ALU latency.
+//
+// Saturated batches are not replayed at all.  The voxels next to the sensor collect one update
+// per ray (65 k for a 64 x 1024 scan), all of them far in front of the surface (sdf >> trunc):
+// once the voxel's distance sits at +trunc, an update with sdf >= 2 trunc leaves it there
+//   new_sdf = (sdf uw + trunc w) / (w + uw) >= trunc (1 + uw / (w + uw)) (1 - 4.1 eps) > trunc
+// (float rounding of the two products, the sum, the weight sum and the division; needs
+// uw / (w + uw) > 4.2 eps, guaranteed by uw >= 2^-20 max_weight) -> fminf(trunc, .) = trunc exactly.
+// The weight recurrence w <- min(max_weight, w + uw) is an exact integer sum when w and all uw of
+// the batch are integer valued and stay below 2^24 (voxgraph integrates with constant weight 1),
+// so a whole batch collapses to w += sum(uw) as long as the cap is not reached inside it.
+// Everything else (first updates, dropped-off weights, the cap) takes the sequential replay, so
+// the result stays bit-identical to the single-threaded reference
+// (tests/test_gpu_tsdf.py::test_deterministic_mode_bit_exact_dense_scans).
 __global__ void __launch_bounds__(128)
 tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ vals,
                        unsigned total, float2* __restrict__ dw, float trunc, float max_weight,
-                       const unsigned* __restrict__ long_heads, const unsigned* __restrict__ n_long) {
+                       const unsigned* __restrict__ long_heads, const unsigned* __restrict__ n_long,
+                       unsigned long long* __restrict__ fast_batches) {
   const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (w >= *n_long) return;
   const unsigned head = long_heads[w];
   const unsigned key = keys[head];
   float2 v = dw[key];
+  const float uw_floor = max_weight * 9.5367431640625e-07f;  // 2^-20 max_weight
+  unsigned n_fast = 0;
   // software pipeline: the next batch's tuples are in flight while the current batch is replayed
   unsigned j = head + lane;
   bool mine = j < total && keys[j] == key;
@@ -372,16 +420,35 @@ tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restri
     const unsigned m = __ballot_sync(0xffffffffu, mine);
     const int cnt = __popc(m);  // the matching lanes form a prefix (keys are sorted)
     if (cnt == 32) {
-      // full batch: stage all 32 tuples in registers first so the shuffles stay off the
-      // serial (distance, weight) recurrence
-      float sx[32], sy[32];
+      // ---- saturated batch? (warp-uniform test)
+      bool fast = false;
+      if (v.x == trunc && v.y == rintf(v.y) && v.y >= 0.f) {
+        const bool lane_ok = u.x >= 2.0f * trunc && u.y >= uw_floor && u.y == rintf(u.y);
+        if (__all_sync(0xffffffffu, lane_ok)) {
+          float sum = u.y;   // integers: the float sum is exact below 2^24
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        sx[k] = __shfl_sync(0xffffffffu, u.x, k);
-        sy[k] = __shfl_sync(0xffffffffu, u.y, k);
+          for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+          const float wn = v.y + sum;
+          if (wn <= max_weight && wn < 16777216.0f) {
+            v.y = wn;        // every partial sum is exact and below the cap: min() never bites
+            fast = true;
+          }
+        }
       }
+      if (fast) {
+        ++n_fast;
+      } else {
+        // full batch: stage all 32 tuples in registers first so the shuffles stay off the
+        // serial (distance, weight) recurrence
+        float sx[32], sy[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) tsdf_apply(trunc, max_weight, sx[k], sy[k], v.x, v.y);
+        for (int k = 0; k < 32; ++k) {
+          sx[k] = __shfl_sync(0xffffffffu, u.x, k);
+          sy[k] = __shfl_sync(0xffffffffu, u.y, k);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tsdf_apply(trunc, max_weight, sx[k], sy[k], v.x, v.y);
+      }
     } else {
       for (int k = 0; k < cnt; ++k) {
         const float sx = __shfl_sync(0xffffffffu, u.x, k);
@@ -393,11 +460,15 @@ tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restri
     mine = mine_n;
     u = u_n;
   }
-  if (lane == 0) dw[key] = v;
+  if (lane == 0) {
+    dw[key] = v;
+    if (n_fast && fast_batches) atomicAdd(fast_batches, (unsigned long long)n_fast);
+  }
 }
 
 __global__ void __launch_bounds__(128)
 tsdf_integrate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
+                      int32_t* __restrict__ block_idx, int* __restrict__ counters, int capacity,
                       float2* __restrict__ dw, unsigned long long* __restrict__ stats,
                       unsigned long long* __restrict__ start_set,
                       unsigned long long* __restrict__ obs_set) {
@@ -427,9 +498,9 @@ tsdf_integrate_kernel(TsdfParams P, const float* __restrict__ pts, VgxHash hash,
           const int b0 = (int)(g[0] >> sh), b1 = (int)(g[1] >> sh), b2 = (int)(g[2] >> sh);
           if (!(b0 == lb0 && b1 == lb1 && b2 == lb2)) {
             lb0 = b0; lb1 = b1; lb2 = b2;
-            slot = vgx_hash_find(hash, b0, b1, b2);
+            slot = tsdf_get_or_alloc<true>(hash, block_idx, counters, capacity, b0, b1, b2);
           }
-          if (slot < 0) continue;  // capacity overflow in pass 1
+          if (slot < 0) continue;  // capacity exhausted (reported by the host)
           const int lin = (int)(g[0] & vmask) + (((int)(g[1] & vmask)) << sh) + (((int)(g[2] & vmask)) << (2 * sh));
           update_tsdf_voxel(P, origin, pG, g, weight, dw + (size_t)slot * vpb + lin);
           ++n_upd;
@@ -468,7 +539,7 @@ extern "C" void vgx_tsdf_config_default(vgx_tsdf_config* c) {
   c->start_voxel_subsampling_factor = 2.0f;
   c->max_consecutive_ray_collisions = 2;
   c->mode = 0;
-  c->deterministic = 1;  // mode 0 applies updates in ray order by default
+  c->deterministic = 1;  // ignored: mode 0 is always ray ordered
 }
 
 extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7], int n,
@@ -517,28 +588,26 @@ extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7],
   if (P.cfg.mode == 1) VGX_CUDA(c, cudaMemsetAsync(d_start, 0xff, 2 * set_bytes, stream));
   const int blocks_before = s->n_blocks;
   const unsigned grid = (unsigned)((n + 127) / 128);
-  {
-    VgxLaunchScope scope(c, 3);
-    TsdfParams Pa = P;
-    tsdf_allocate_kernel<<<grid, 128, 0, stream>>>(Pa, d_pts, s->hash, s->d_block_idx, s->d_counters,
-                                                  s->cap_blocks);
-  }
-  if (P.cfg.mode == 0 && P.cfg.deterministic) {
-    // ---- ray-ordered path: count -> scan -> emit -> stable sort by voxel -> sequential apply
-    const size_t cnt_bytes = ((sizeof(unsigned) * ((size_t)n + 1)) + 255) & ~(size_t)255;
-    size_t scan_tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned*)nullptr, (unsigned*)nullptr, n + 1, stream);
+  if (P.cfg.mode == 0) {
+    // ---- ray-ordered path: allocate -> count -> scan -> emit -> stable sort by voxel -> apply
+    {
+      VgxLaunchScope scope(c, 3);
+      tsdf_allocate_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, s->d_block_idx, s->d_counters,
+                                                    s->cap_blocks);
+    }
+    const size_t cnt_bytes = ((sizeof(unsigned) * ((size_t)n + 2)) + 255) & ~(size_t)255;
+    const size_t scan_tmp = ((vgx_scan_tmp_count((size_t)n) * sizeof(unsigned)) + 255) & ~(size_t)255;
     rc = c->ensure_sort(2 * cnt_bytes + scan_tmp + 256);
     if (rc != VGX_OK) return rc;
     unsigned* d_counts = (unsigned*)c->d_sort;
     unsigned* d_offsets = (unsigned*)((char*)c->d_sort + cnt_bytes);
-    void* d_scan_tmp = (char*)c->d_sort + 2 * cnt_bytes;
+    unsigned* d_scan_tmp = (unsigned*)((char*)c->d_sort + 2 * cnt_bytes);
     unsigned total = 0;
     {
-      VgxLaunchScope scope(c, 2, 2);
-      VGX_CUDA(c, cudaMemsetAsync(d_counts, 0, cnt_bytes, stream));
+      VgxLaunchScope scope(c, 2, 1);
       tsdf_count_kernel<<<grid, 128, 0, stream>>>(P, d_pts, d_counts);
-      cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp, d_counts, d_offsets, n + 1, stream);
+      rc = vgx_exclusive_scan_u32(c, d_counts, d_offsets, (size_t)n, d_scan_tmp);   // hand-written, 3 launches
+      if (rc != VGX_OK) return rc;
     }
     VGX_CUDA(c, cudaMemcpyAsync(&total, d_offsets + n, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     VGX_CUDA(c, cudaStreamSynchronize(stream));
@@ -580,12 +649,14 @@ extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7],
         const unsigned max_long = total / VGX_TSDF_LONG_SEGMENT + 1;
         tsdf_apply_long_kernel<<<(max_long + 3) / 4, 128, 0, stream>>>(
             k_out, v_out, total, s->d_dw, P.cfg.default_truncation_distance, P.cfg.max_weight, d_heads,
-            d_nlong);
+            d_nlong, d_stats + 3);
       }
     }
   } else {
+    // ---- Fast scheduling: one kernel, blocks allocated on demand
     VgxLaunchScope scope(c, 2);
-    tsdf_integrate_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, s->d_dw, d_stats, d_start, d_obs);
+    tsdf_integrate_kernel<<<grid, 128, 0, stream>>>(P, d_pts, s->hash, s->d_block_idx, s->d_counters,
+                                                   s->cap_blocks, s->d_dw, d_stats, d_start, d_obs);
   }
   VGX_CUDA(c, cudaGetLastError());
   unsigned long long h_stats[4];
@@ -599,10 +670,13 @@ extern "C" int vgx_tsdf_integrate(vgx_ctx* c, uint32_t id, const float T_G_C[7],
   st.rays_cast = (int64_t)h_stats[1];
   st.voxel_updates = (int64_t)h_stats[2];
   st.blocks_allocated = s->n_blocks - blocks_before;
+  st.saturated_batches = (int64_t)h_stats[3];
   if (stats) *stats = st;
   if (overflow) {
+    // keys without a brick must not stay in the table: rebuild it from the blocks that exist
     int fixed[2] = {s->n_blocks, 0};
     cudaMemcpyAsync(s->d_counters, fixed, sizeof(fixed), cudaMemcpyHostToDevice, stream);
+    vgx_submap_rebuild_hash(c, s);
     cudaStreamSynchronize(stream);
     VGX_FAIL(c, VGX_ERR_CAPACITY, "vgx_tsdf_integrate: submap block capacity exhausted");
   }

@@ -57,16 +57,20 @@ struct VgxHash {
 };
 
 #ifdef __CUDACC__
+// Read-only lookup (finished layers / kernels that do not insert concurrently).  At most
+// table-size probes: a completely full table (capacity overflow) ends the search instead of
+// spinning.  Entries with val < 0 (unmapped / overflowed) read as "no block".
 __device__ __forceinline__ int vgx_hash_find(const VgxHash& h, int bx, int by, int bz) {
   const uint64_t key = vgx_pack_key(bx, by, bz);
   uint32_t i = vgx_hash_index(bx, by, bz, h.mask);
-  for (;;) {
+  for (uint32_t n = 0; n <= h.mask; ++n) {
     const int4 e = __ldg(reinterpret_cast<const int4*>(h.entries + i));
     const uint64_t k = (uint64_t)(uint32_t)e.x | ((uint64_t)(uint32_t)e.y << 32);
-    if (k == key) return e.z;
+    if (k == key) return e.z < 0 ? -1 : e.z;
     if (k == VGX_EMPTY_KEY) return -1;
     i = (i + 1) & h.mask;
   }
+  return -1;
 }
 #endif
 
@@ -102,11 +106,14 @@ struct VgxSubmap {
   // neighbourhood (corner i: x = bit2, y = bit1, z = bit0; apron across bricks baked in),
   // NaN where the voxel is unobserved or its block missing. One 32-byte sector per point.
   float* d_view = nullptr;         // cap x vps^3 x 8
+  float2* d_esdf = nullptr;        // ESDF bricks (distance, observed 1/0), n_blocks x vps^3 (vgx_submap_generate_esdf)
+  float* d_view_esdf = nullptr;    // registration view of the ESDF bricks
   int* d_counters = nullptr;       // [0] = n_blocks (device), [1] = overflow flag
   // Dense block index over the AABB of the allocated blocks (finished submaps): slot or -1.
   // Small enough to be staged in shared memory by the registration kernel; the hash stays
   // the general structure (integration, view construction, sparse/huge submaps).
   int32_t* d_grid = nullptr;
+  uint16_t* d_grid16 = nullptr;   // 16-bit copy (0xFFFF = no block), padded to a multiple of 16 bytes
   int grid_min[3] = {0, 0, 0};
   int grid_dim[3] = {0, 0, 0};
   VgxPoints points[2];
@@ -162,7 +169,8 @@ struct vgx_ctx {
   size_t p2p_cap = 0;              // doubles per buffer
   unsigned long long p2p_epoch = 0;
   bool p2p_ready = false;
-  bool p2p_fused = false;          // one-launch assemble + exchange (VGX_P2P_FUSED=1)
+  bool p2p_fused = true;           // one-launch assemble + exchange (VGX_P2P_FUSED=0: two launches)
+  long long p2p_timeout_cycles = 0;
 
   void set_error(const std::string& e) { error = e; }
   VgxSubmap* find(uint32_t id) {
@@ -196,6 +204,11 @@ struct VgxLaunchScope {
 };
 
 int vgx_submap_build_grid(vgx_ctx* ctx, VgxSubmap* s);
+// registration view (octets) of `bricks` (n_blocks x vps^3 (distance, weight/observed)) into `view`
+int vgx_submap_build_view(vgx_ctx* ctx, VgxSubmap* s, const float2* bricks, float* view);
+// clears the block hash and re-inserts the first s->n_blocks blocks (after a capacity overflow
+// left keys without a brick behind)
+int vgx_submap_rebuild_hash(vgx_ctx* ctx, VgxSubmap* s);
 // hand-written exclusive scan (extract.cu): out[0..n], out[n] = total; d_tmp: vgx_scan_tmp_count(n) words
 int vgx_exclusive_scan_u32(vgx_ctx* c, const unsigned* d_in, unsigned* d_out, size_t n, unsigned* d_tmp);
 size_t vgx_scan_tmp_count(size_t n);
@@ -207,18 +220,42 @@ void vgx_graph_invalidate_registration(vgx_ctx* ctx);
 // NCCL (dlopen'ed, nccl_dyn.cpp)
 int vgx_nccl_allreduce_sum_f64(vgx_ctx* ctx, double* d_buf, size_t count);
 
-// NVLink peer exchange (p2p.cu)
-// Starts an exchange epoch: returns where to assemble this evaluation's partial and the
-// signal descriptor the producing kernel's last CTA uses to notify every peer.
+// NVLink peer exchange (p2p.cu): PUSH all-gather + local reduce.
+// Every rank owns a CUDA-IPC exported region [flags 256 B | slot[parity 2][source rank 8][cap]].
+// An evaluation (epoch e, parity e & 1): the assembly kernel stores each value of the rank's partial
+// straight into slot[parity][rank] of EVERY rank's region (posted NVLink writes), fences, and its
+// last CTA stores e into flag[rank] of every region; the receiver waits for its own n flags and
+// adds its n local slots in rank order (no load ever crosses NVLink; bit-identical on all ranks).
+struct VgxP2PPush {
+  double* dst[8];   // where this rank's partial goes: one destination per rank (n == 1: local buffer)
+  int n;
+};
 struct VgxP2PSignal {
   unsigned long long* flags[8];  // flag array of every rank (peer-mapped)
   unsigned long long epoch;
   int* counter;                  // local ticket counter (finished CTAs)
   int nranks, rank;              // nranks == 0: disabled
 };
-int vgx_p2p_begin(vgx_ctx* ctx, size_t count, double** send_buf, VgxP2PSignal* sig);
-int vgx_p2p_gather(vgx_ctx* ctx, double* d_out, size_t count);     // wait for all ranks + sum into d_out
-// current epoch's buffer of every rank + the local timeout word (for the fused kernel)
-void vgx_p2p_gather_sources(vgx_ctx* ctx, const void* bufs[8], int** timeout_flag);
+struct VgxP2PGather {
+  const double* slot[8];         // this epoch's local slots, one per source rank
+  const unsigned long long* flags;   // own flag array
+  int* timeout_flag;
+  long long timeout_cycles;
+  unsigned long long epoch;
+  int nranks;
+};
+int vgx_p2p_begin(vgx_ctx* ctx, size_t count, VgxP2PPush* push, VgxP2PSignal* sig, VgxP2PGather* gat);
+int vgx_p2p_gather(vgx_ctx* ctx, const VgxP2PGather& gat, double* d_out, size_t count);  // separate-launch variant
 void vgx_p2p_free(vgx_ctx* ctx);
-int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out
+int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out (the flag is cleared)
+#ifdef __CUDACC__
+// waits for the n flags (thread 0 of the CTA), returns false on timeout
+__device__ __forceinline__ bool vgx_p2p_wait(const VgxP2PGather& G) {
+  const volatile unsigned long long* mine = G.flags;
+  const long long t0 = clock64();
+  for (int r = 0; r < G.nranks; ++r)
+    while (mine[r] < G.epoch)
+      if (clock64() - t0 > G.timeout_cycles) { *G.timeout_flag = 1; return false; }
+  return true;
+}
+#endif

@@ -78,6 +78,7 @@ class RegistrationCostFunction {
     int registration_point_type = VGX_POINTS_ISOSURFACE;
     float sampling_ratio = -1;
     double no_correspondence_cost = 0;
+    bool use_esdf_distance = false;  // h:35 (reference default true): needs Context-side generateEsdf
   };
   RegistrationCostFunction(const Context& ctx, SubmapID reference, SubmapID reading, const Config& config)
       : ctx_(ctx), reference_(reference), reading_(reading) {
@@ -85,6 +86,7 @@ class RegistrationCostFunction {
     cfg_.registration_point_type = config.registration_point_type;
     cfg_.sampling_ratio = config.sampling_ratio;
     cfg_.no_correspondence_cost = config.no_correspondence_cost;
+    cfg_.use_esdf_distance = config.use_esdf_distance ? 1 : 0;
     ctx_.check(vgx_reg_num_residuals(ctx_.get(), reference_, &cfg_, &num_residuals_));
   }
   int num_residuals() const { return num_residuals_; }
@@ -314,6 +316,7 @@ class PoseGraph {
       rcs[k].registration_point_type = registration_cfgs_[k].registration_point_type;
       rcs[k].sampling_ratio = registration_cfgs_[k].sampling_ratio;
       rcs[k].no_correspondence_cost = registration_cfgs_[k].no_correspondence_cost;
+      rcs[k].use_esdf_distance = registration_cfgs_[k].use_esdf_distance ? 1 : 0;
     }
     ctx_.check(vgx_graph_set_registration_constraints_v(ctx_.get(), (int)ra.size(), ra.data(), rb.data(),
                                                         rcs.data()));
@@ -329,6 +332,22 @@ class PoseGraph {
   std::vector<SolverSummary> solver_summaries_;
   bool dirty_ = true;
 };
+
+// PoseGraphInterface::updateOverlappingSubmapList (pose_graph_interface.cpp:109-147) over
+// VoxgraphSubmap::overlapsWith (voxgraph_submap.cpp:245-278).  poses: T_mission_submap as
+// [qw qx qy qz tx ty tz] per submap (float, as cblox stores them).
+inline std::vector<std::pair<SubmapID, SubmapID>> findOverlappingSubmaps(
+    Context& ctx, const std::vector<SubmapID>& ids, const std::vector<std::array<float, 7>>& poses) {
+  if (ids.size() != poses.size()) throw std::invalid_argument("findOverlappingSubmaps: one pose per submap");
+  const int n = (int)ids.size();
+  const int cap = std::max(1, n * (n - 1) / 2);
+  std::vector<uint32_t> out(2 * (size_t)cap);
+  int np = 0;
+  ctx.check(vgx_find_overlapping_pairs(ctx.get(), n, ids.data(), n ? poses[0].data() : nullptr, cap, out.data(), &np));
+  std::vector<std::pair<SubmapID, SubmapID>> pairs;
+  for (int k = 0; k < np; ++k) pairs.emplace_back(out[2 * k], out[2 * k + 1]);
+  return pairs;
+}
 
 // PointcloudIntegrator::integratePointcloud (pointcloud_integrator.cpp:23-90) minus the ROS/PCL
 // message conversion: points_C is the voxblox::Pointcloud (n x 3 floats, sensor frame).
@@ -346,7 +365,15 @@ class PointcloudIntegrator {
     ctx_.check(vgx_tsdf_integrate(ctx_.get(), submap, T_submap_sensor, n, points_C, nullptr, &config_, &st));
     return st;
   }
+  // VoxgraphSubmap::finishSubmap (voxgraph_submap.cpp:84-107): registration view, then - with a
+  // filter - the registration points (relevant voxels + isosurface vertices), the surface OBB and
+  // the isosurface block list, all on the device
   void finishSubmap(SubmapID id) { ctx_.check(vgx_submap_finish(ctx_.get(), id)); }
+  void finishSubmap(SubmapID id, const vgx_registration_filter& filter) {
+    ctx_.check(vgx_submap_finish(ctx_.get(), id));
+    if (filter.use_esdf_distance) ctx_.check(vgx_submap_generate_esdf(ctx_.get(), id, nullptr, nullptr));  // cpp:86
+    ctx_.check(vgx_submap_extract_points(ctx_.get(), id, &filter));
+  }
 
  private:
   Context& ctx_;
