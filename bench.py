@@ -134,7 +134,7 @@ def build_stream(kind, n_scans, rank=0, wait_s=900.0):
     kind = "lidar": 64 x 1024 beams @ 10 Hz; "rgbd": 640 x 480 depth @ 30 Hz (<= 5 m).  Odometry =
     ground truth + integrated drift.  Host-side numpy ray casting, forked workers, cached in /tmp."""
     from voxgraph_b200 import synth
-    path = "/tmp/vgx_stream_v2_%s_%d.pkl" % (kind, n_scans)
+    path = "/tmp/vgx_stream_v3_%s_%d.pkl" % (kind, n_scans)
 
     def load():
         try:
@@ -163,7 +163,7 @@ def build_stream(kind, n_scans, rank=0, wait_s=900.0):
     yaw = np.arctan2(np.gradient(y), np.gradient(x)) if n_scans > 1 else np.zeros(1)
     gt = np.stack([x, y, np.full(n_scans, 1.2), yaw], -1)
     odo = gt.copy()
-    drift = np.cumsum(rng.normal(0, 1.0, (n_scans, 4)) * np.array([0.004, 0.004, 0.0005, 0.0004]), 0)
+    drift = np.cumsum(rng.normal(0, 1.0, (n_scans, 4)) * np.array([0.02, 0.02, 0.001, 0.002]), 0)
     odo += drift
     import multiprocessing as mp
     workers = max(1, min(64, (os.cpu_count() or 2) - 2))

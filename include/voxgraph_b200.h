@@ -134,6 +134,17 @@ int vgx_submap_info(vgx_ctx* ctx, uint32_t submap_id, float* voxel_size, int* vo
 int vgx_submap_download(vgx_ctx* ctx, uint32_t submap_id, int max_blocks, int32_t* block_idx,
                         float* distance, float* weight, int* n_blocks);
 
+/* Device-to-device hand-over of a finished submap between two contexts (BASELINE configs[4]: one
+ * GPU integrates, the other registers; the finished submap crosses NVLink once).  peek: read-only
+ * device pointers of the resident bricks (block indices n x 3 int32, voxels n x vps^3 x
+ * {distance, weight} float) - valid until the submap is modified or freed; the caller moves them
+ * with its own transport (ncclSend / cudaMemcpyPeer).  upload_device: same as vgx_submap_upload but
+ * from device memory of this context's GPU, interleaved (distance, weight) voxels. */
+int vgx_submap_peek_device(vgx_ctx* ctx, uint32_t submap_id, const int32_t** d_block_idx,
+                           const float** d_distance_weight, int* n_blocks);
+int vgx_submap_upload_device(vgx_ctx* ctx, uint32_t submap_id, float voxel_size, int voxels_per_side,
+                             int n_blocks, const int32_t* d_block_idx, const float* d_distance_weight);
+
 /* Registration points of a submap = WeightedSampler<RegistrationPoint> items
  * (include/voxgraph/frontend/submap_collection/registration_point.h:6-12).
  * point_type: 0 = kVoxels, 1 = kIsosurfacePoints (voxgraph_submap.h RegistrationPointType). */
@@ -291,6 +302,13 @@ void vgx_solver_options_default(vgx_solver_options* o);
  * stay the graph's current poses. */
 int vgx_graph_solve(vgx_ctx* ctx, const vgx_solver_options* opts, double* xyzyaw_out,
                     vgx_solver_summary* summary);
+
+/* PoseGraph::getEdgeCovarianceMap (pose_graph.cpp:117-163): the 4 x 4 covariance blocks
+ * Cov(x_a, x_b) (row-major, rows = parameters of a) that ceres::Covariance reports for the requested
+ * submap pairs: blocks of (J^T J)^-1 over the free nodes at the current poses; zero for a constant
+ * node.  Fails (VGX_ERR_INVALID) where Covariance::Compute returns false (rank-deficient J). */
+int vgx_graph_edge_covariances(vgx_ctx* ctx, int m, const uint32_t* ids_a, const uint32_t* ids_b,
+                               double* covariances /* m x 16 */);
 
 /* ------------------------------------------------------------------ multi-GPU */
 /* One process per GPU. Registration constraints are sharded over the ranks of the

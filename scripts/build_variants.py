@@ -9,15 +9,12 @@ sys.path.insert(0, ROOT)
 from voxgraph_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "all_on_b5": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
-    "all_on_b6": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
-    "all_on_b4": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=4"],
-    "no_ldg256": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_LDG256=0"],
-    "no_earlyout": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_EARLYOUT=0"],
-    "no_skipgram": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_SKIPGRAM=0"],
-    "all_off": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5", "-DVGX_REG_LDG256=0", "-DVGX_REG_EARLYOUT=0", "-DVGX_REG_SKIPGRAM=0"],
-    "all_on_t256_b2": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=2"],
-    "all_on_t256_b3": ["-DVGX_REG_THREADS=256", "-DVGX_REG_MIN_BLOCKS=3"],
+    "b5": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=5"],
+    "b6": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=6"],
+    "b7": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=7"],
+    "b8": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=8"],
+    "t64_b12": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=12"],
+    "t64_b16": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=16"],
 }
 
 if __name__ == "__main__":

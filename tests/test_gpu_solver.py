@@ -251,3 +251,42 @@ def test_solver_errors(ctx, oracle):
         pg.addRegistrationConstraint(api.RegistrationConstraintConfig(0, 5))
     with pytest.raises(ValueError):
         pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(0, 1, np.zeros(4), -np.eye(4)))
+
+
+def test_edge_covariances_match_inverse_normal_matrix(ctx, oracle, small_scene):
+    """PoseGraph::getEdgeCovarianceMap (pose_graph.cpp:117-163): blocks of (J^T J)^-1 over the free
+    nodes, as ceres::Covariance reports them, vs numpy on the oracle's J^T J."""
+    from voxgraph_b200 import api
+    sc = small_scene
+    for s in sc.submaps:
+        ctx.upload_synth_submap(s)
+    pg = api.PoseGraph(ctx); og = oracle.Graph()
+    layers = [oracle.Layer.from_blocks(s.voxel_size, s.vps, s.block_idx, s.distance, s.weight) for s in sc.submaps]
+    n = len(sc.submaps)
+    for i in range(n):
+        pg.addSubmapNode(api.SubmapNodeConfig(i, sc.poses_init[i], set_constant=(i == 0)))
+        og.add_node(i, sc.poses_init[i], constant=(i == 0))
+    L = oracle.sqrt_information(sc.odom_information)
+    for (i, j, t, y) in sc.odometry:
+        pg.addRelativePoseConstraint(api.RelativePoseConstraintConfig(i, j, np.array([*t, y]), sc.odom_information))
+        og.add_relative(i, j, t, y, L)
+    for (i, j) in sc.pairs:
+        pg.addRegistrationConstraint(api.RegistrationConstraintConfig(i, j))
+        a, b = sc.submaps[i], sc.submaps[j]
+        og.add_registration(i, j, layers[j], a.points_xyz, a.points_distance, a.points_weight)
+        og.add_registration(j, i, layers[i], b.points_xyz, b.points_distance, b.points_weight)
+    ok, cost, g, H = og.eval(num_threads=2)
+    free = np.arange(4, 4 * n)                      # node 0 is constant
+    Cov = np.linalg.inv(H[np.ix_(free, free)])
+    pairs = [(1, 2), (2, 1), (3, 3), (1, n - 1), (0, 2), (2, 0)]
+    got = pg.getEdgeCovarianceMap(pairs)
+    scale = np.abs(Cov).max()
+    for (a, b) in pairs:
+        if a == 0 or b == 0:
+            assert np.all(got[(a, b)] == 0)          # constant block: zero covariance
+            continue
+        want = Cov[4 * (a - 1):4 * a, 4 * (b - 1):4 * b]
+        assert np.abs(got[(a, b)] - want).max() <= 1e-7 * scale, (a, b)
+    assert np.allclose(got[(1, 2)], got[(2, 1)].T, atol=1e-9 * scale)
+    with pytest.raises(api.VgxError):
+        ctx.graph_edge_covariances([1], [99])

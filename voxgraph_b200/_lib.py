@@ -104,7 +104,8 @@ EXPORTS = [
     "vgx_registration_filter_default", "vgx_submap_extract_points", "vgx_submap_finish_ex",
     "vgx_submap_num_points", "vgx_submap_download_points", "vgx_submap_surface_obb",
     "vgx_find_overlapping_pairs", "vgx_esdf_config_default", "vgx_submap_generate_esdf",
-    "vgx_submap_download_esdf",
+    "vgx_submap_download_esdf", "vgx_graph_edge_covariances", "vgx_submap_peek_device",
+    "vgx_submap_upload_device",
 ]
 
 _lib = None
@@ -173,6 +174,9 @@ def load():
     L.vgx_esdf_config_default.restype = None
     L.vgx_submap_generate_esdf.argtypes = [vp, u32, C.POINTER(EsdfConfig), C.POINTER(i32)]
     L.vgx_submap_download_esdf.argtypes = [vp, u32, i32, pf, pf, C.POINTER(i32)]
+    L.vgx_graph_edge_covariances.argtypes = [vp, i32, pu32, pu32, pd]
+    L.vgx_submap_peek_device.argtypes = [vp, u32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(i32)]
+    L.vgx_submap_upload_device.argtypes = [vp, u32, C.c_float, i32, i32, C.c_void_p, C.c_void_p]
     L.vgx_submap_info.argtypes = [vp, u32, pf, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.vgx_submap_draw_samples.argtypes = [vp, u32, i32, i32, pi32]
     L.vgx_graph_num_registration_residuals.argtypes = [vp, C.POINTER(C.c_int64),

@@ -104,6 +104,16 @@ class Context:
     def submap_finish(self, submap_id):
         self._check(self._L.vgx_submap_finish(self._h, int(submap_id)))
 
+    def submap_peek_device(self, submap_id):
+        """(device pointer of block indices, device pointer of (distance, weight) voxels, n_blocks)."""
+        pi = C.c_void_p(); pd = C.c_void_p(); n = C.c_int(0)
+        self._check(self._L.vgx_submap_peek_device(self._h, int(submap_id), C.byref(pi), C.byref(pd), C.byref(n)))
+        return pi.value, pd.value, n.value
+
+    def submap_upload_device(self, submap_id, voxel_size, vps, n_blocks, d_block_idx_ptr, d_dw_ptr):
+        self._check(self._L.vgx_submap_upload_device(self._h, int(submap_id), float(voxel_size), int(vps),
+                                                     int(n_blocks), C.c_void_p(d_block_idx_ptr), C.c_void_p(d_dw_ptr)))
+
     def registration_filter(self, **kw):
         f = RegistrationFilter()
         self._L.vgx_registration_filter_default(C.byref(f))
@@ -329,6 +339,13 @@ class Context:
         out = np.zeros(n_constraints)
         self._check(self._L.vgx_graph_registration_costs(self._h, _p(out, C.c_double)))
         return out
+
+    def graph_edge_covariances(self, ids_a, ids_b):
+        a = np.ascontiguousarray(ids_a, np.uint32); b = np.ascontiguousarray(ids_b, np.uint32)
+        cov = np.zeros((len(a), 4, 4))
+        self._check(self._L.vgx_graph_edge_covariances(self._h, len(a), _p(a, C.c_uint32), _p(b, C.c_uint32),
+                                                       _p(cov, C.c_double)))
+        return cov
 
     def solver_options(self, **kw):
         o = SolverOptions()
@@ -592,6 +609,13 @@ class PoseGraph:
 
     def getSubmapPoses(self):
         return {i: v[0].copy() for i, v in self._nodes.items() if i < FRAME_NODE_ID_BASE}
+
+    def getEdgeCovarianceMap(self, submap_id_pairs):
+        """pose_graph.cpp:117-163: {(first, second): 4x4 covariance} for the requested pairs."""
+        self._sync()
+        pairs = [(int(a), int(b)) for (a, b) in submap_id_pairs]
+        cov = self.ctx.graph_edge_covariances([p[0] for p in pairs], [p[1] for p in pairs])
+        return {p: cov[k] for k, p in enumerate(pairs)}
 
     def getSolverSummaries(self):
         return self.solver_summaries

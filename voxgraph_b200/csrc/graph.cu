@@ -1512,6 +1512,183 @@ extern "C" int vgx_graph_registration_costs(vgx_ctx* c, double* per_constraint) 
   return VGX_OK;
 }
 
+// ------------------------------------------------------------------ edge covariances
+// PoseGraph::getEdgeCovarianceMap (pose_graph.cpp:117-163): ceres::Covariance blocks
+// Cov(x_a, x_b) = rows of a, columns of b of (J^T J)^-1 over the free parameter blocks at the current
+// poses (no LM damping, no Jacobi scaling, no loss function); constant blocks have zero covariance.
+// Dense reduced H -> Cholesky (the solver's factorisation kernels) -> two triangular solves per
+// requested column.
+__global__ void cov_build_kernel(const double* __restrict__ packed, const int* __restrict__ red,
+                                 const int* __restrict__ block_nodes, int N, int E, int n,
+                                 double* __restrict__ A) {
+  const int M = n + 1;
+  const double* D = packed + PACK_HDR + 4 * (size_t)N;
+  const double* O = D + 16 * (size_t)N;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int t = tid; t < N * 16; t += stride) {
+    const int node = t >> 4, r = (t >> 2) & 3, c = t & 3;
+    const int off = red[node];
+    if (off < 0 || r < c) continue;
+    A[(size_t)(off + c) * M + off + r] = D[16 * (size_t)node + 4 * r + c];
+  }
+  for (int t = tid; t < E * 16; t += stride) {
+    const int b = t >> 4, r = (t >> 2) & 3, c = t & 3;
+    const int ni = block_nodes[2 * b], nj = block_nodes[2 * b + 1];
+    const int oi = red[ni], oj = red[nj];
+    if (oi < 0 || oj < 0) continue;
+    A[(size_t)(oi + r) * M + (oj + c)] = O[16 * (size_t)b + 4 * r + c];   // lower triangle: oj > oi
+  }
+}
+
+// one CTA per requested column c: x = (L L^T)^-1 e_c.  L: lower, column-major, leading dimension n+1.
+__global__ void __launch_bounds__(256)
+cov_column_kernel(const double* __restrict__ A, int n, const int* __restrict__ cols, double* __restrict__ X) {
+  extern __shared__ double sx[];   // n
+  __shared__ double s_red[8];
+  const int M = n + 1, c = cols[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += blockDim.x) sx[i] = (i == c) ? 1.0 : 0.0;
+  __syncthreads();
+  // forward: L y = e_c (y_i = 0 for i < c)
+  for (int i = c; i < n; ++i) {
+    double acc = 0;
+    for (int k = c + tid; k < i; k += blockDim.x) acc += A[(size_t)k * M + i] * sx[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+      sx[i] = (sx[i] - t) / A[(size_t)i * M + i];
+    }
+    __syncthreads();
+  }
+  // backward: L^T x = y
+  for (int i = n - 1; i >= 0; --i) {
+    double acc = 0;
+    for (int k = i + 1 + tid; k < n; k += blockDim.x) acc += A[(size_t)i * M + k] * sx[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+      sx[i] = (sx[i] - t) / A[(size_t)i * M + i];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += blockDim.x) X[(size_t)blockIdx.x * n + i] = sx[i];
+}
+
+extern "C" int vgx_graph_edge_covariances(vgx_ctx* c, int m, const uint32_t* ids_a, const uint32_t* ids_b,
+                                          double* cov) {
+  VgxGraph* g = nullptr;
+  int rc = prepare(c, &g);
+  if (rc != VGX_OK) return rc;
+  if (m < 0 || (m > 0 && (!ids_a || !ids_b || !cov))) return VGX_ERR_INVALID;
+  if (m == 0) return VGX_OK;
+  if (g->zero_weight) VGX_FAIL(c, VGX_ZERO_WEIGHT, "a registration constraint has zero summed weight (Evaluate == false)");
+  const int N = g->N, n = g->n_free;
+  std::vector<int> red(N, -1);
+  {
+    int o = 0;
+    for (int i = 0; i < N; ++i)
+      if (!g->constant[i]) { red[i] = o; o += 4; }
+  }
+  // distinct columns: the 4 parameters of every second node that is free
+  std::vector<int> col_of(N, -1), cols;
+  std::vector<std::pair<int, int>> pr(m);
+  for (int k = 0; k < m; ++k) {
+    auto ia = g->index.find(ids_a[k]);
+    auto ib = g->index.find(ids_b[k]);
+    if (ia == g->index.end() || ib == g->index.end())
+      VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_graph_edge_covariances: graph contains no node for a requested submap");
+    pr[k] = {ia->second, ib->second};
+    const int b = ib->second;
+    if (red[b] >= 0 && col_of[b] < 0) {
+      col_of[b] = (int)cols.size();
+      for (int q = 0; q < 4; ++q) cols.push_back(red[b] + q);
+    }
+  }
+  for (int k = 0; k < 16 * m; ++k) cov[k] = 0.0;   // constant blocks: zero covariance
+  if (n == 0 || cols.empty()) return VGX_OK;
+  cudaStream_t st = c->stream;
+  rc = eval_enqueue(c, g, g->d_x, g->d_packed[0], true, false);
+  if (rc != VGX_OK) return rc;
+  const size_t M = (size_t)n + 1;
+  VGX_CUDA(c, cudaMemsetAsync(g->d_A, 0, sizeof(double) * M * M, st));
+  {
+    VgxLaunchScope s(c, 4);
+    const int nthreads = 16 * (N + g->E);
+    cov_build_kernel<<<std::min(296, (nthreads + 255) / 256), 256, 0, st>>>(g->d_packed[0], g->d_red_offset,
+                                                                          g->d_block_nodes, N, g->E, n, g->d_A);
+  }
+  // factorise with the solver's kernels (the rhs row n of the augmented matrix stays zero)
+  VGX_CUDA(c, cudaMemsetAsync(g->d_state, 0, sizeof(LmState), st));
+  {
+    LmState init;
+    memset(&init, 0, sizeof(init));
+    init.step_valid = 1;
+    VGX_CUDA(c, cudaMemcpyAsync(g->d_state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    VGX_CUDA(c, cudaStreamSynchronize(st));
+  }
+  {
+    VgxLaunchScope s(c, 4);
+    int coop = 0, sms = 0, per_sm = 0, coop_grid = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const size_t chol_smem = sizeof(double) * ((size_t)CH_NB * 33 + (size_t)std::max(n + 1 - CH_NB, 1) * 33);
+    if (n > 256 && coop &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_coop_kernel, 256, 0) == cudaSuccess && per_sm > 0) {
+      const int tiles = ((n + 1 + CH_NB - 1) / CH_NB) * ((n + CH_NB - 1) / CH_NB);
+      coop_grid = std::max(1, std::min(sms * std::min(per_sm, 2), std::max(tiles / 2, (n + 256) / 256)));
+    }
+    if (coop_grid > 0) {
+      int n_arg = n;
+      void* args[] = {(void*)&g->d_A, (void*)&n_arg, (void*)&g->d_state};
+      VGX_CUDA(c, cudaLaunchCooperativeKernel((void*)chol_coop_kernel, dim3(coop_grid), dim3(256), args, 0, st));
+    } else {
+      if (chol_smem > 227 * 1024)
+        VGX_FAIL(c, VGX_ERR_CAPACITY, "pose graph too large for the single-CTA dense factorisation");
+      VGX_CUDA(c, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+      chol_kernel<<<1, 1024, chol_smem, st>>>(g->d_A, n, g->d_state);
+    }
+  }
+  VGX_CUDA(c, cudaGetLastError());
+  // inverse columns
+  const size_t ncols = cols.size();
+  rc = c->ensure_scratch(sizeof(int) * ncols + 256 + sizeof(double) * ncols * (size_t)n);
+  if (rc != VGX_OK) return rc;
+  int* d_cols = (int*)c->d_scratch;
+  double* d_X = (double*)((char*)c->d_scratch + ((sizeof(int) * ncols + 255) & ~(size_t)255));
+  VGX_CUDA(c, cudaMemcpyAsync(d_cols, cols.data(), sizeof(int) * ncols, cudaMemcpyHostToDevice, st));
+  if (sizeof(double) * (size_t)n > 48 * 1024)
+    VGX_CUDA(c, cudaFuncSetAttribute(cov_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * (size_t)n)));
+  {
+    VgxLaunchScope s(c, 4);
+    cov_column_kernel<<<(unsigned)ncols, 256, sizeof(double) * (size_t)n, st>>>(g->d_A, n, d_cols, d_X);
+  }
+  VGX_CUDA(c, cudaGetLastError());
+  std::vector<double> X(ncols * (size_t)n);
+  LmState hs;
+  VGX_CUDA(c, cudaMemcpyAsync(X.data(), d_X, sizeof(double) * X.size(), cudaMemcpyDeviceToHost, st));
+  VGX_CUDA(c, cudaMemcpyAsync(&hs, g->d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  VGX_CUDA(c, cudaStreamSynchronize(st));
+  if (!hs.step_valid)   // ceres::Covariance::Compute returns false on a rank-deficient Jacobian
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_graph_edge_covariances: J^T J is not positive definite (rank deficient)");
+  for (int k = 0; k < m; ++k) {
+    const int a = pr[k].first, b = pr[k].second;
+    if (red[a] < 0 || red[b] < 0) continue;
+    for (int r = 0; r < 4; ++r)
+      for (int q = 0; q < 4; ++q)
+        cov[16 * (size_t)k + 4 * r + q] = X[(size_t)(col_of[b] + q) * n + red[a] + r];
+  }
+  return VGX_OK;
+}
+
 extern "C" void vgx_solver_options_default(vgx_solver_options* o) {
   if (!o) return;
   o->max_num_iterations = 50;

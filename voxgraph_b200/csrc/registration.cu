@@ -4,6 +4,7 @@
 #include "registration_kernels.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 // ------------------------------------------------------------------ emit mode
 // One thread per registration point; writes the normalised residual and the two 1x4
@@ -147,8 +148,11 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                              (stage_grid ? (uint32_t)T.grid_bytes : 0u);
       mbar_expect_tx(tbar, bytes);
       tma_load_1d(smem_u32(&s_C), constraints + T.constraint, (uint32_t)sizeof(RegConstraintDev), tbar);
-      tma_load_1d(smem_u32(&s_P), poses + T.constraint, (uint32_t)sizeof(RegPoseConst), tbar);
       if (stage_grid) tma_load_1d(smem_u32(s_grid), T.grid16, (uint32_t)T.grid_bytes, tbar);
+      // the pose blocks are the only input the preceding kernel (pose set-up) writes: everything
+      // above was independent of it (programmatic dependent launch)
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      tma_load_1d(smem_u32(&s_P), poses + T.constraint, (uint32_t)sizeof(RegPoseConst), tbar);
     }
     if (stage_grid) grid_of = T.constraint;
     const int n_units = (T.count + 31) >> 5;
@@ -339,6 +343,9 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
 __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ constraints,
                                       const double* __restrict__ x, RegPoseConst* __restrict__ poses,
                                       int n_constraints) {
+  // programmatic dependent launch: the reduce kernel may start its prologue (tile records, TMA of the
+  // descriptors, block grids and first point units) while the pose blocks are still being computed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_constraints) return;
   RegPoseConst P;
@@ -358,15 +365,26 @@ void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const 
                            const int* tile_begin, int* counters, double* partials, double* csum,
                            int grid_capacity, bool jacobian) {
   if (n_ctas <= 0) return;
-  const size_t smem = sizeof(uint16_t) * (size_t)grid_capacity;
+  // launched with programmatic stream serialisation: its CTAs may start while the pose set-up kernel
+  // is still running; they block at griddepcontrol.wait before touching the pose blocks
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(VGX_REG_THREADS);
+  cfg.dynamicSmemBytes = sizeof(uint16_t) * (size_t)grid_capacity;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const char* no_pdl = getenv("VGX_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (jacobian)
-    reg_reduce_kernel<true><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
-                                                                  tile_begin, counters, partials, csum,
-                                                                  grid_capacity);
+    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<true>, cons, poses, tiles, cta_tile_begin, tile_begin, counters,
+                       partials, csum, grid_capacity);
   else
-    reg_reduce_kernel<false><<<n_ctas, VGX_REG_THREADS, smem, st>>>(cons, poses, tiles, cta_tile_begin,
-                                                                   tile_begin, counters, partials, csum,
-                                                                   grid_capacity);
+    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<false>, cons, poses, tiles, cta_tile_begin, tile_begin, counters,
+                       partials, csum, grid_capacity);
 }
 
 int vgx_reg_resident_ctas(int device, int grid_capacity) {

@@ -10,7 +10,7 @@ struct RegPoseConst;
 #define VGX_REG_THREADS 128        // 4 warps per CTA, each with its own TMA ring + software pipeline
 #endif
 #ifndef VGX_REG_MIN_BLOCKS
-#define VGX_REG_MIN_BLOCKS 5       // resident CTAs per SM the register budget is sized for
+#define VGX_REG_MIN_BLOCKS 7       // resident CTAs per SM the register budget is sized for (72 registers)
 #endif
 #ifndef VGX_REG_RING
 #define VGX_REG_RING 4             // point-slice ring slots per warp (units in flight = RING - 1)
@@ -25,7 +25,7 @@ struct RegPoseConst;
 #define VGX_REG_SKIPGRAM 1         // no Gram stage for a unit without a single correspondence
 #endif
 #ifndef VGX_REG_HW_TILE_UNITS
-#define VGX_REG_HW_TILE_UNITS 0    // > 0: one CTA per tile of that many units (hardware scheduling); 0: persistent
+#define VGX_REG_HW_TILE_UNITS 32   // > 0: one CTA per tile of that many units (hardware scheduling); 0: persistent
 #endif
 #define VGX_REG_UNIT 32            // points per unit = one warp iteration; tiles are cut on unit boundaries
 #ifndef VGX_REG_STREAM_OCTETS

@@ -379,6 +379,42 @@ extern "C" int vgx_submap_upload(vgx_ctx* c, uint32_t id, float voxel_size, int 
   return vgx_submap_build_grid(c, s);
 }
 
+extern "C" int vgx_submap_peek_device(vgx_ctx* c, uint32_t id, const int32_t** d_block_idx,
+                                      const float** d_dw, int* n_blocks) {
+  if (!c) return VGX_ERR_INVALID;
+  VgxSubmap* s = c->find(id);
+  if (!s) VGX_FAIL(c, VGX_ERR_NOT_FOUND, "vgx_submap_peek_device: unknown submap");
+  VGX_CUDA(c, cudaSetDevice(c->device));
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));   // the caller reads the bricks on its own stream
+  if (d_block_idx) *d_block_idx = s->d_block_idx;
+  if (d_dw) *d_dw = reinterpret_cast<const float*>(s->d_dw);
+  if (n_blocks) *n_blocks = s->n_blocks;
+  return VGX_OK;
+}
+
+extern "C" int vgx_submap_upload_device(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int n_blocks,
+                                        const int32_t* d_block_idx, const float* d_dw) {
+  if (!c) return VGX_ERR_INVALID;
+  if (n_blocks < 0 || (n_blocks > 0 && (!d_block_idx || !d_dw)))
+    VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_upload_device: null input");
+  VgxSubmap* s = nullptr;
+  int rc = alloc_submap(c, id, voxel_size, vps, n_blocks, true, &s);
+  if (rc != VGX_OK) return rc;
+  s->n_blocks = n_blocks;
+  s->finished = true;
+  if (n_blocks == 0) return VGX_OK;
+  const size_t nvox = (size_t)n_blocks * s->vox_per_block;
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_block_idx, d_block_idx, sizeof(int32_t) * 3 * n_blocks, cudaMemcpyDeviceToDevice, c->stream));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_dw, d_dw, sizeof(float2) * nvox, cudaMemcpyDeviceToDevice, c->stream));
+  VGX_CUDA(c, cudaMemcpyAsync(s->d_counters, &s->n_blocks, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  hash_insert_kernel<<<(n_blocks + 127) / 128, 128, 0, c->stream>>>(s->hash, s->d_block_idx, n_blocks);
+  c->launches++;
+  rc = vgx_submap_build_view(c, s, s->d_dw, s->d_view);
+  if (rc != VGX_OK) return rc;
+  VGX_CUDA(c, cudaStreamSynchronize(c->stream));   // the source buffers are the caller's
+  return vgx_submap_build_grid(c, s);
+}
+
 extern "C" int vgx_submap_create(vgx_ctx* c, uint32_t id, float voxel_size, int vps, int capacity) {
   if (!c) return VGX_ERR_INVALID;
   if (capacity <= 0) VGX_FAIL(c, VGX_ERR_INVALID, "vgx_submap_create: capacity must be > 0");

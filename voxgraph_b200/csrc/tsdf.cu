@@ -391,9 +391,10 @@ tsdf_apply_kernel(const unsigned* __restrict__ keys, const float2* __restrict__ 
 // (float rounding of the two products, the sum, the weight sum and the division; needs
 // uw / (w + uw) > 4.2 eps, guaranteed by uw >= 2^-20 max_weight) -> fminf(trunc, .) = trunc exactly.
 // The weight recurrence w <- min(max_weight, w + uw) is an exact integer sum when w and all uw of
-// the batch are integer valued and stay below 2^24 (voxgraph integrates with constant weight 1),
-// so a whole batch collapses to w += sum(uw) as long as the cap is not reached inside it.
-// Everything else (first updates, dropped-off weights, the cap) takes the sequential replay, so
+// the batch are integer valued and stay below 2^24 (voxgraph integrates with constant weight 1):
+// a whole batch collapses to w <- min(max_weight, w + sum(uw)) - exact partial sums until the cap
+// is crossed, pinned at the cap from then on (a voxel already at the cap simply stays there).
+// Everything else (first updates, dropped-off weights, fractional weights) takes the sequential replay, so
 // the result stays bit-identical to the single-threaded reference
 // (tests/test_gpu_tsdf.py::test_deterministic_mode_bit_exact_dense_scans).
 __global__ void __launch_bounds__(128)
@@ -422,17 +423,18 @@ tsdf_apply_long_kernel(const unsigned* __restrict__ keys, const float2* __restri
     if (cnt == 32) {
       // ---- saturated batch? (warp-uniform test)
       bool fast = false;
-      if (v.x == trunc && v.y == rintf(v.y) && v.y >= 0.f) {
-        const bool lane_ok = u.x >= 2.0f * trunc && u.y >= uw_floor && u.y == rintf(u.y);
+      const bool capped = v.y == max_weight;   // w <- min(max_weight, w + uw) is stuck at the cap
+      if (v.x == trunc && (capped || (v.y == rintf(v.y) && v.y >= 0.f && max_weight < 16777216.0f))) {
+        const bool lane_ok = u.x >= 2.0f * trunc && u.y >= uw_floor && (capped || u.y == rintf(u.y));
         if (__all_sync(0xffffffffu, lane_ok)) {
-          float sum = u.y;   // integers: the float sum is exact below 2^24
+          if (!capped) {
+            float sum = u.y;   // integers: every partial sum below the cap is exact (< 2^24)
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          const float wn = v.y + sum;
-          if (wn <= max_weight && wn < 16777216.0f) {
-            v.y = wn;        // every partial sum is exact and below the cap: min() never bites
-            fast = true;
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            // step k: w_k = min(max_weight, w_{k-1} + u_k); exact until the cap is crossed, then pinned
+            v.y = fminf(max_weight, v.y + sum);
           }
+          fast = true;
         }
       }
       if (fast) {
