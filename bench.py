@@ -239,7 +239,6 @@ def stream_leg(ctx, api, st, voxel_size, scans_per_submap, peak, cpu_scans=3):
         err_opt = float(np.abs((opt[:, :2] - opt[0, :2]) - (gt0[:, :2] - gt0[0, :2])).mean())
         # the reference's parameter_tolerance 3e-3 is relative to |x| (tens of metres here): a step
         # below ~5 cm ends the solve unapplied.  One more solve at 1e-8 shows what registration recovers.
-        m.updateRegistrationConstraints()
         m.pose_graph.solver_options.parameter_tolerance = 1e-8
         m.pose_graph.solver_options.function_tolerance = 1e-12
         m.pose_graph.solver_options.max_num_iterations = 50

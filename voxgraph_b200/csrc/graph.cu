@@ -72,9 +72,13 @@ struct VgxGraph {
   double* d_partials = nullptr;
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
-  int* d_counters = nullptr;    // per-constraint finished-tile counters
+  int* d_counters = nullptr;    // (unused)
+  int* d_tile_order = nullptr;  // one-CTA-per-tile mode: CTA b runs tile d_tile_order[b] (longest first)
+  int* d_tile_cost = nullptr;   // SM cycles each tile took in the latest evaluation
+  bool hw_tiles = false;
+  int evals_since_order = -1;   // -1: no cost measured yet since the tables were built
   int* d_csr_begin = nullptr;   // N + E + 1
-  int2* d_csr_items = nullptr;  // (blk, role)
+  int4* d_csr_items = nullptr;  // (source, role, first tile, end tile)
   int* d_block_nodes = nullptr; // E x 2
   int* d_red_offset = nullptr;  // N: reduced offset or -1
   double* d_x = nullptr;
@@ -94,6 +98,8 @@ struct VgxGraph {
 static void free_tables(VgxGraph* g) {
   cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_cta_tile_begin);
   cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
+  cudaFree(g->d_tile_order); cudaFree(g->d_tile_cost);
+  g->d_tile_order = nullptr; g->d_tile_cost = nullptr;
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
   cudaFree(g->d_packed[0]); cudaFree(g->d_packed[1]);
@@ -175,6 +181,38 @@ __device__ __forceinline__ void rel_eval(const VgxRelEdge& E, const double* __re
   }
 }
 
+// The reduce kernel leaves one row of 21 sums per TILE; a constraint's sums are its tiles' rows added
+// in tile order, times factor^2 (cpp:274-291).  Doing this here, in the consumer, keeps tickets and
+// fences out of the hot kernel and is bit-reproducible whatever order the tiles ran in.
+struct RegSums {
+  const double* partials;
+  const int* tile_begin;
+  const RegConstraintDev* cons;
+};
+// entry e of the tiles [t0, t1), added in tile order (four loads in flight)
+__device__ __forceinline__ double reg_tile_sum(const double* __restrict__ partials, int t0, int t1, int e) {
+  const double* p = partials + (size_t)t0 * VGX_REG_NSTRIDE + e;
+  double s = 0;
+  int t = t0;
+  for (; t + 4 <= t1; t += 4, p += 4 * VGX_REG_NSTRIDE) {
+    const double v0 = __ldcg(p), v1 = __ldcg(p + VGX_REG_NSTRIDE), v2 = __ldcg(p + 2 * VGX_REG_NSTRIDE),
+                 v3 = __ldcg(p + 3 * VGX_REG_NSTRIDE);
+    s = (((s + v0) + v1) + v2) + v3;
+  }
+  for (; t < t1; ++t, p += VGX_REG_NSTRIDE) s += __ldcg(p);
+  return s;
+}
+__device__ __forceinline__ double reg_constraint_sum(const RegSums& R, int c, int e) {
+  const double f = R.cons[c].factor;
+  return reg_tile_sum(R.partials, R.tile_begin[c], R.tile_begin[c + 1], e) * (f * f);
+}
+
+// per-constraint sums for the host (vgx_graph_registration_costs): one warp per constraint
+__global__ void reg_csum_kernel(RegSums R, int n, double* __restrict__ csum) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c < n && lane < VGX_REG_NSUM) csum[(size_t)c * VGX_REG_NSTRIDE + lane] = reg_constraint_sum(R, c, lane);
+}
+
 // Assembly of the packed normal equations, one 4-warp CTA per output block (N diagonal, E
 // off-diagonal, +1 for the cost). Lanes 0..15 own the 4x4 entries, lanes 16..19 the
 // gradient of a diagonal block. Contributions are summed in list order -> bit-reproducible.
@@ -205,19 +243,37 @@ __device__ __forceinline__ void assemble_signal(const VgxP2PSignal& sig) {
 // Work of one output block `ob` (N diagonal, E off-diagonal, ob == N + E: the cost) by one
 // 4-warp CTA: warp w sums items w, w+4, ...; the four partial sums are combined in warp order
 // -> bit-reproducible. Ends with a __syncthreads() so it can be called in a loop.
-__device__ __forceinline__ void assemble_block(int ob, const double* __restrict__ csum,
+#define VGX_ASM_CHUNK 24   // items whose constraint sums are staged in shared memory at a time
+__device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
                                                const VgxRelEdge* __restrict__ rel,
                                                const double* __restrict__ x,
                                                const int* __restrict__ csr_begin,
-                                               const int2* __restrict__ items,
+                                               const int4* __restrict__ items,
                                                const VgxP2PPush& push, int N, int E, int n_reg,
-                                               int n_rel, int exclude_reg, double (*s_part)[20]) {
+                                               int n_rel, int exclude_reg, double (*s_part)[20],
+                                               double (*s_sums)[VGX_REG_NSUM]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ob == N + E) {
-    // cost = 1/2 sum r^2
+    // cost = 1/2 sum r^2: thread t takes constraints t, t + 128, ... four at a time (their loads overlap)
     double a = 0;
-    if (!exclude_reg)
-      for (int c = threadIdx.x; c < n_reg; c += 128) a += csum[(size_t)c * VGX_REG_NSTRIDE + 20];
+    if (!exclude_reg) {
+      for (int c0 = threadIdx.x; c0 < n_reg; c0 += 4 * 128) {
+        int t0[4], t1[4];
+        double f[4], v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + 128 * k;
+          const bool in = c < n_reg;
+          t0[k] = in ? __ldg(sums.tile_begin + c) : 0;
+          t1[k] = in ? __ldg(sums.tile_begin + c + 1) : 0;
+          f[k] = in ? sums.cons[c].factor : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = reg_tile_sum(sums.partials, t0[k], t1[k], 20);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a += v[k] * (f[k] * f[k]);
+      }
+    }
     for (int e = threadIdx.x; e < n_rel; e += 128) {
       RelEval R;
       rel_eval(rel[e], x, R);
@@ -242,52 +298,68 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
   const bool diag = ob < N;
   const int r4 = (lane >> 2) & 3, c4 = lane & 3;
   double acc = 0;
-  for (int i = i0 + warp; i < i1; i += 4) {
-    const int2 it = items[i];
-    // (row, col) of the residual block's 8x8 this lane needs; lanes 16..19: gradient row
-    int row, col;
-    if (lane < 16) {
-      switch (it.y) {
-        case 0: row = r4; col = c4; break;
-        case 1: row = 4 + r4; col = 4 + c4; break;
-        case 2: row = r4; col = 4 + c4; break;
-        default: row = 4 + r4; col = c4; break;
+  for (int base = i0; base < i1; base += VGX_ASM_CHUNK) {
+    const int nc = min(VGX_ASM_CHUNK, i1 - base);
+    // ---- phase A: the 21 sums of every registration item of the chunk, all 128 threads: thread k
+    //      owns (item k / 21, entry k % 21); an item's row of each tile is one coalesced 168-byte read
+    if (!exclude_reg) {
+      for (int k = threadIdx.x; k < nc * VGX_REG_NSUM; k += 128) {
+        const int j = k / VGX_REG_NSUM, e = k - j * VGX_REG_NSUM;
+        const int4 it = __ldg(items + base + j);
+        if (it.x >= 0) {
+          const double f = sums.cons[it.x].factor;
+          s_sums[j][e] = reg_tile_sum(sums.partials, it.z, it.w, e) * (f * f);
+        }
       }
-    } else {
-      row = (it.y == 0 ? 0 : 4) + (lane & 3);
-      col = -1;
     }
-    if (it.x >= 0) {
-      if (exclude_reg) continue;
-      const double sv = (lane < VGX_REG_NSUM) ? csum[(size_t)it.x * VGX_REG_NSTRIDE + lane] : 0.0;
-      // 8-vector j8 = (j0, j1, j2, j3, -j0, -j1, -j2, j4): map component a -> (m, sign)
-      const int ma = (row < 4) ? row : (row == 7 ? 4 : row - 4);
-      const double sa = (row >= 4 && row < 7) ? -1.0 : 1.0;
-      int idx;
-      double sgn = sa;
-      if (col >= 0) {
-        const int mb = (col < 4) ? col : (col == 7 ? 4 : col - 4);
-        sgn *= (col >= 4 && col < 7) ? -1.0 : 1.0;
-        const int p = min(ma, mb), q = max(ma, mb);
-        idx = p * 5 - (p * (p - 1)) / 2 + (q - p);
+    __syncthreads();
+    // ---- phase B: warp w expands items w, w + 4, ... of the chunk in list order
+    for (int j = warp; j < nc; j += 4) {
+      const int4 it = __ldg(items + base + j);
+      // (row, col) of the residual block's 8x8 this lane needs; lanes 16..19: gradient row
+      int row, col;
+      if (lane < 16) {
+        switch (it.y) {
+          case 0: row = r4; col = c4; break;
+          case 1: row = 4 + r4; col = 4 + c4; break;
+          case 2: row = r4; col = 4 + c4; break;
+          default: row = 4 + r4; col = c4; break;
+        }
       } else {
-        idx = 15 + ma;
+        row = (it.y == 0 ? 0 : 4) + (lane & 3);
+        col = -1;
       }
-      const double v = __shfl_sync(0xffffffffu, sv, idx);
-      acc += sgn * v;
-    } else {
-      RelEval R;
-      rel_eval(rel[-it.x - 1], x, R);
-      double v = 0;
-      if (col >= 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.J[k][col];
+      if (it.x >= 0) {
+        if (exclude_reg) continue;
+        // 8-vector j8 = (j0, j1, j2, j3, -j0, -j1, -j2, j4): map component a -> (m, sign)
+        const int ma = (row < 4) ? row : (row == 7 ? 4 : row - 4);
+        const double sa = (row >= 4 && row < 7) ? -1.0 : 1.0;
+        int idx;
+        double sgn = sa;
+        if (col >= 0) {
+          const int mb = (col < 4) ? col : (col == 7 ? 4 : col - 4);
+          sgn *= (col >= 4 && col < 7) ? -1.0 : 1.0;
+          const int p = min(ma, mb), q = max(ma, mb);
+          idx = p * 5 - (p * (p - 1)) / 2 + (q - p);
+        } else {
+          idx = 15 + ma;
+        }
+        acc += sgn * s_sums[j][idx];
       } else {
+        RelEval R;
+        rel_eval(rel[-it.x - 1], x, R);
+        double v = 0;
+        if (col >= 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.r[k];
+          for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.J[k][col];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v += R.J[k][row] * R.r[k];
+        }
+        acc += v;
       }
-      acc += v;
     }
+    __syncthreads();   // the chunk's sums are consumed before the next chunk overwrites them
   }
   if (lane < 20) s_part[warp][lane] = acc;
   __syncthreads();
@@ -305,12 +377,17 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
 }
 
 __global__ void __launch_bounds__(128)
-assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
+assemble_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
-                const int2* __restrict__ items, VgxP2PPush push, int N, int E, int n_reg,
+                const int4* __restrict__ items, VgxP2PPush push, int N, int E, int n_reg,
                 int n_rel, int exclude_reg, VgxP2PSignal sig) {
   __shared__ double s_part[4][20];
-  assemble_block(blockIdx.x, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
+  __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
+  // programmatic dependent of the reduce kernel: scheduled while that grid drains, blocked here until
+  // it has completed and its tile sums are visible
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // next evaluation's pose set-up
+  assemble_block(blockIdx.x, sums, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part, s_sums);
   assemble_signal(sig);
 }
 
@@ -321,15 +398,18 @@ assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ 
 // CTAs can never starve a CTA that still has to produce: phase 1 never waits, phase 2 only waits
 // on flags that phase 1 of every rank sets.
 __global__ void __launch_bounds__(128)
-assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
+assemble_exchange_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
                          const double* __restrict__ x, const int* __restrict__ csr_begin,
-                         const int2* __restrict__ items, VgxP2PPush push, int N, int E,
+                         const int4* __restrict__ items, VgxP2PPush push, int N, int E,
                          int n_reg, int n_rel, int exclude_reg, VgxP2PSignal sig, VgxP2PGather gat,
                          double* __restrict__ out, int count) {
   __shared__ double s_part[4][20];
+  __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
   __shared__ int s_ok;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // see assemble_kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int ob = blockIdx.x; ob <= N + E; ob += gridDim.x)
-    assemble_block(ob, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
+    assemble_block(ob, sums, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part, s_sums);
   assemble_signal(sig);
   // ---- phase 2: wait for every rank's flag in OUR region, then add our slice of the local slots
   if (threadIdx.x == 0) {
@@ -1086,8 +1166,14 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   // that many units, ONE CTA PER TILE, dealt to the SMs by the hardware block scheduler as
   // resident CTAs retire (dynamic balancing at no instruction cost; the per-CTA set-up latency
   // hides behind the other resident CTAs).  0: persistent CTAs with an equal static cut.
+  // Tile size: at most VGX_REG_HW_TILE_UNITS units, fewer when the problem is small, so that there
+  // are at least ~2 tiles per resident CTA slot (a 3-pair streaming graph still fills the machine).
   int hw_units = VGX_REG_HW_TILE_UNITS;
+  if (hw_units > 0)
+    hw_units = (int)std::min<int64_t>(hw_units, std::max<int64_t>(4, (U + 2 * (int64_t)n_ctas_max - 1) / (2 * (int64_t)n_ctas_max)));
   if (const char* e = getenv("VGX_REG_HW_TILE_UNITS")) hw_units = atoi(e);
+  g->hw_tiles = false;
+  g->evals_since_order = -1;
   if (hw_units > 0) {
     for (int k = 0; k < g->n_local; ++k) {
       tile_begin.push_back((int)tiles.size());
@@ -1099,6 +1185,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
       }
     }
     g->n_ctas = (int)tiles.size();
+    g->hw_tiles = true;
     cta_tile_begin.resize(tiles.size() + 1);
     for (size_t k = 0; k <= tiles.size(); ++k) cta_tile_begin[k] = (int)k;
   } else {
@@ -1164,10 +1251,12 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   for (int e = 0; e < g->n_rel_local; ++e) add_items(-(e + 1), g->rel[e].a, g->rel[e].b);
   for (int k = 0; k < g->n_local; ++k) add_items(k, cons[k].ref_node, cons[k].read_node);
   std::vector<int> csr_begin(N + g->E + 1, 0);
-  std::vector<int2> items;
+  std::vector<int4> items;   // a registration item carries its constraint's tile range
   for (int ob = 0; ob < N + g->E; ++ob) {
     csr_begin[ob] = (int)items.size();
-    items.insert(items.end(), lists[ob].begin(), lists[ob].end());
+    for (const int2& it : lists[ob])
+      items.push_back(it.x >= 0 ? make_int4(it.x, it.y, tile_begin[it.x], tile_begin[it.x + 1])
+                                : make_int4(it.x, it.y, 0, 0));
   }
   csr_begin[N + g->E] = (int)items.size();
 
@@ -1185,6 +1274,13 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   if (e == cudaSuccess) e = upload_vec(&g->d_tiles, tiles, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_tile_begin, tile_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_cta_tile_begin, cta_tile_begin, st);
+  static const char* lpt_env = getenv("VGX_REG_LPT");
+  if (g->hw_tiles && !(lpt_env && lpt_env[0] == '0')) {
+    std::vector<int> ident(tiles.size()), zero(tiles.size(), 0);
+    for (size_t k = 0; k < tiles.size(); ++k) ident[k] = (int)k;
+    if (e == cudaSuccess) e = upload_vec(&g->d_tile_order, ident, st);
+    if (e == cudaSuccess) e = upload_vec(&g->d_tile_cost, zero, st);
+  }
   if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
@@ -1197,10 +1293,6 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_poses, sizeof(RegPoseConst) * g->n_local);
   dmalloc((void**)&g->d_partials, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_tiles);
   dmalloc((void**)&g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local);
-  dmalloc((void**)&g->d_counters, sizeof(int) * (size_t)g->n_local);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_counters, 0, std::max<size_t>(sizeof(int) * (size_t)g->n_local, 4), st);
-  // a constraint without points owns no tile: its sums must read as zero
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->d_csum, 0, std::max<size_t>(sizeof(double) * VGX_REG_NSTRIDE * (size_t)g->n_local, 8), st);
   dmalloc((void**)&g->d_xc, sizeof(double) * 4 * N);
   dmalloc((void**)&g->d_packed[0], sizeof(double) * g->packed_len);
   dmalloc((void**)&g->d_packed[1], sizeof(double) * g->packed_len);
@@ -1227,6 +1319,14 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   cudaStream_t st = c->stream;
   const bool do_reg = !exclude_reg && g->n_local > 0;
   if (do_reg) {
+    // refresh the longest-first tile order from the cost measured by the previous evaluation: before
+    // the second evaluation on new tables, then every 32nd (the poses move little inside a solve)
+    if (g->d_tile_order && g->n_tiles > 1 && (g->evals_since_order == -2 || g->evals_since_order >= 32)) {
+      VgxLaunchScope s(c, 5);
+      vgx_launch_reg_order(st, g->d_tile_cost, g->n_tiles, g->d_tile_order);
+      g->evals_since_order = 0;
+    }
+    if (g->evals_since_order >= 0) ++g->evals_since_order;
     {
       VgxLaunchScope s(c, 5);
       vgx_launch_reg_pose_setup(st, g->d_cons, d_x, g->d_poses, g->n_local);
@@ -1234,9 +1334,9 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     {
       VgxLaunchScope s(c, 0);
       vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_ctas, g->d_cta_tile_begin,
-                            g->d_tile_begin, g->d_counters, g->d_partials, g->d_csum, g->grid_capacity,
-                            jacobian);
+                            g->d_tile_order, g->d_tile_cost, g->d_partials, g->grid_capacity, jacobian);
     }
+    if (g->evals_since_order < 0) g->evals_since_order = -2;   // a cost has been measured now
   }
   // multi-rank peer path: the assembly pushes this rank's partial into every rank's region
   const bool p2p = c->nranks > 1 && c->p2p_ready;
@@ -1248,6 +1348,20 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   memset(&gat, 0, sizeof(gat));
   push.n = 1;
   push.dst[0] = d_packed;
+  RegSums sums;
+  sums.partials = g->d_partials; sums.tile_begin = g->d_tile_begin; sums.cons = g->d_cons;
+  // both assembly kernels are launched as programmatic dependents of what precedes them on the stream
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  static const char* no_pdl = getenv("VGX_NO_PDL");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(128);
+  cfg.stream = st;
+  cfg.attrs = pdl;
+  cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  const int excl = do_reg ? 0 : 1;
   if (p2p) {
     int rc = vgx_p2p_begin(c, g->packed_len, &push, &sig, &gat);
     if (rc != VGX_OK) return rc;
@@ -1265,19 +1379,19 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     const int grid = std::min(g->N + g->E + 1, std::min(resident, 592));
     {
       VgxLaunchScope s(c, 5);
-      assemble_exchange_kernel<<<grid, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
-                                                    g->d_csr_items, push, g->N, g->E, g->n_local,
-                                                    g->n_rel_local, do_reg ? 0 : 1, sig, gat, d_packed,
-                                                    (int)g->packed_len);
+      cfg.gridDim = dim3((unsigned)grid);
+      cudaLaunchKernelEx(&cfg, assemble_exchange_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x,
+                         (const int*)g->d_csr_begin, (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local,
+                         g->n_rel_local, excl, sig, gat, d_packed, (int)g->packed_len);
     }
     VGX_CUDA(c, cudaGetLastError());
     return VGX_OK;
   }
   {
     VgxLaunchScope s(c, 5);
-    assemble_kernel<<<g->N + g->E + 1, 128, 0, st>>>(g->d_csum, g->d_rel, d_x, g->d_csr_begin,
-                                                     g->d_csr_items, push, g->N, g->E, g->n_local,
-                                                     g->n_rel_local, do_reg ? 0 : 1, sig);
+    cfg.gridDim = dim3((unsigned)(g->N + g->E + 1));
+    cudaLaunchKernelEx(&cfg, assemble_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x, (const int*)g->d_csr_begin,
+                       (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, sig);
   }
   VGX_CUDA(c, cudaGetLastError());
   if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len);
@@ -1503,6 +1617,12 @@ extern "C" int vgx_graph_registration_costs(vgx_ctx* c, double* per_constraint) 
   if (rc != VGX_OK) return rc;
   const int P = (int)g->reg_ref.size();
   std::vector<double> cs((size_t)g->n_local * VGX_REG_NSTRIDE + 1);
+  if (g->n_local > 0) {
+    RegSums sums;
+    sums.partials = g->d_partials; sums.tile_begin = g->d_tile_begin; sums.cons = g->d_cons;
+    reg_csum_kernel<<<(g->n_local + 3) / 4, 128, 0, c->stream>>>(sums, g->n_local, g->d_csum);
+    c->launches++;
+  }
   if (g->n_local > 0)
     VGX_CUDA(c, cudaMemcpyAsync(cs.data(), g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * g->n_local,
                                 cudaMemcpyDeviceToHost, c->stream));

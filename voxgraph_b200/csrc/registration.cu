@@ -97,9 +97,8 @@ template <bool kJacobian>
 __global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
-                  const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_begin,
-                  int* __restrict__ counters, double* __restrict__ partials,
-                  double* __restrict__ csum, int grid_capacity) {
+                  const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_order,
+                  int* __restrict__ tile_cost, double* __restrict__ partials, int grid_capacity) {
   constexpr int kWarps = VGX_REG_THREADS / 32;
   constexpr int kRing = VGX_REG_RING;
   __shared__ __align__(128) float s_ring[kWarps][kRing][5][32];
@@ -109,7 +108,6 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
   __shared__ double s_gram[kWarps][64];
   __shared__ __align__(16) RegConstraintDev s_C;
   __shared__ __align__(16) RegPoseConst s_P;
-  __shared__ int s_last;
   extern __shared__ __align__(16) uint16_t s_grid[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
@@ -119,6 +117,9 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
     if (warp == 0) mbar_init(smem_u32(&s_tbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // the assembly kernel may be scheduled as soon as every CTA of this grid has started; it blocks in
+  // griddepcontrol.wait until this grid has completed and its partials are visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
   const uint32_t ring0 = smem_u32(&s_ring[warp][0][0][0]);
   const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
@@ -130,7 +131,13 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
   int grid_of = -1;  // constraint whose block grid is currently staged
 
   uint32_t tseq = 0;  // tiles staged by this CTA (parity of the tile barrier)
-  for (int tile = cta_tile_begin[blockIdx.x]; tile < cta_tile_begin[blockIdx.x + 1]; ++tile, ++tseq) {
+  // one CTA per tile: CTA b runs tile_order[b] (longest-first order from the measured cost of an earlier
+  // evaluation: the hardware hands CTAs out in index order, so the expensive tiles start first and the
+  // tail of the grid is made of cheap ones); persistent mode: CTA b walks its run of tiles
+  int tile_first, tile_end;
+  if (tile_order) { tile_first = __ldg(tile_order + blockIdx.x); tile_end = tile_first + 1; }
+  else { tile_first = cta_tile_begin[blockIdx.x]; tile_end = cta_tile_begin[blockIdx.x + 1]; }
+  for (int tile = tile_first; tile < tile_end; ++tile, ++tseq) {
     // the 32-byte tile record is all a thread needs to start the bulk copies
     const int4 rec0 = __ldg(reinterpret_cast<const int4*>(tiles + tile));
     const ulonglong2 rec1 = __ldg(reinterpret_cast<const ulonglong2*>(tiles + tile) + 1);
@@ -172,6 +179,7 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
         if (j < my_units) issue(j, it + j);
     }
     mbar_wait(tbar, tseq & 1u);   // descriptor, pose block and grid have landed
+    const long long clk0 = clock64();
     const RegPoseConst P = s_P;
     double d0 = 0.0, d1 = 0.0;
     const size_t vox_shift = 3 * s_C.vps_shift;
@@ -290,7 +298,6 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       if (lane == 0) s_gram[warp][0] = d0;
     }
     __syncthreads();
-    const double factor = s_C.factor;
     if (threadIdx.x < VGX_REG_NSUM) {
       // entry e of the 21 sums -> (row, col) of the Gram matrix
       int row = 5, col = 5;
@@ -310,34 +317,52 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
 #pragma unroll
         for (int wv = 0; wv < kWarps; ++wv) s += s_gram[wv][0];
       }
+      // The tile's sums are final here: no ticket, no fence.  The assembly kernel (a programmatic
+      // dependent of this one) adds a constraint's tiles in tile order and applies factor^2
+      // (cpp:274-291) - bit-reproducible whatever order the tiles ran in.
       partials[(size_t)tile * VGX_REG_NSTRIDE + e] = s;
-    }
-    // The last tile of a constraint to finish sums the constraint's partials in tile order
-    // (bit-reproducible) and applies factor^2 (cpp:274-291).
-    const int t0 = tile_begin[T.constraint], t1 = tile_begin[T.constraint + 1];
-    if (t1 - t0 == 1) {
-      if (threadIdx.x < VGX_REG_NSUM)  // single tile: no ticket needed (same thread wrote the partial)
-        csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] =
-            partials[(size_t)tile * VGX_REG_NSTRIDE + threadIdx.x] * (factor * factor);
-    } else {
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const int done = atomicAdd(counters + T.constraint, 1);
-        s_last = (done == t1 - t0 - 1);
-      }
-      __syncthreads();
-      if (s_last) {
-        __threadfence();
-        if (threadIdx.x < VGX_REG_NSUM) {
-          double s = 0;
-          for (int t = t0; t < t1; ++t) s += __ldcg(partials + (size_t)t * VGX_REG_NSTRIDE + threadIdx.x);
-          csum[(size_t)T.constraint * VGX_REG_NSTRIDE + threadIdx.x] = s * (factor * factor);
-        }
-        if (threadIdx.x == 0) counters[T.constraint] = 0;
-      }
+      if (e == 0 && tile_cost) tile_cost[tile] = (int)min(clock64() - clk0, (long long)0x3fffffff);
     }
   }
+}
+
+// Longest-processing-time-first order of the tiles from their measured cost (SM cycles of an earlier
+// evaluation at nearly the same poses): counting sort into 1024 cost classes, most expensive first.
+// One CTA; the order inside a class is arbitrary (the results do not depend on the execution order).
+__global__ void __launch_bounds__(1024)
+reg_order_kernel(const int* __restrict__ cost, int n, int* __restrict__ order) {
+  __shared__ int s_hist[1024];
+  __shared__ int s_scan[1024];
+  __shared__ int s_max;
+  const int t = threadIdx.x;
+  s_hist[t] = 0;
+  if (t == 0) s_max = 1;
+  __syncthreads();
+  int m = 1;
+  for (int i = t; i < n; i += 1024) m = max(m, cost[i]);
+  atomicMax(&s_max, m);
+  __syncthreads();
+  const float scale = 1023.0f / (float)s_max;
+  for (int i = t; i < n; i += 1024) atomicAdd(&s_hist[1023 - min(1023, (int)((float)cost[i] * scale))], 1);
+  __syncthreads();
+  // exclusive scan of the 1024 classes (Hillis-Steele)
+  int v = s_hist[t];
+  s_scan[t] = v;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int add = t >= off ? s_scan[t - off] : 0;
+    __syncthreads();
+    s_scan[t] += add;
+    __syncthreads();
+  }
+  s_hist[t] = s_scan[t] - v;
+  __syncthreads();
+  for (int i = t; i < n; i += 1024)
+    order[atomicAdd(&s_hist[1023 - min(1023, (int)((float)cost[i] * scale))], 1)] = i;
+}
+
+void vgx_launch_reg_order(cudaStream_t st, const int* tile_cost, int n_tiles, int* tile_order) {
+  if (n_tiles > 0) reg_order_kernel<<<1, 1024, 0, st>>>(tile_cost, n_tiles, tile_order);
 }
 
 __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ constraints,
@@ -346,6 +371,10 @@ __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ const
   // programmatic dependent launch: the reduce kernel may start its prologue (tile records, TMA of the
   // descriptors, block grids and first point units) while the pose blocks are still being computed
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // ... and this kernel may itself have been scheduled while the previous evaluation's assembly was
+  // still running: the pose blocks it overwrites were read by that evaluation's reduce kernel, which
+  // has completed once the assembly (its dependent) has
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_constraints) return;
   RegPoseConst P;
@@ -357,13 +386,24 @@ __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ const
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n) {
   if (n <= 0) return;
-  reg_pose_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(cons, x, poses, n);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((n + 127) / 128));
+  cfg.blockDim = dim3(128);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const char* no_pdl = getenv("VGX_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, reg_pose_setup_kernel, cons, x, poses, n);
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
                            const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
-                           const int* tile_begin, int* counters, double* partials, double* csum,
-                           int grid_capacity, bool jacobian) {
+                           const int* tile_order, int* tile_cost, double* partials, int grid_capacity,
+                           bool jacobian) {
   if (n_ctas <= 0) return;
   // launched with programmatic stream serialisation: its CTAs may start while the pose set-up kernel
   // is still running; they block at griddepcontrol.wait before touching the pose blocks
@@ -380,11 +420,11 @@ void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const 
   cfg.attrs = attr;
   cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (jacobian)
-    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<true>, cons, poses, tiles, cta_tile_begin, tile_begin, counters,
-                       partials, csum, grid_capacity);
+    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<true>, cons, poses, tiles, cta_tile_begin, tile_order, tile_cost,
+                       partials, grid_capacity);
   else
-    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<false>, cons, poses, tiles, cta_tile_begin, tile_begin, counters,
-                       partials, csum, grid_capacity);
+    cudaLaunchKernelEx(&cfg, reg_reduce_kernel<false>, cons, poses, tiles, cta_tile_begin, tile_order, tile_cost,
+                       partials, grid_capacity);
 }
 
 int vgx_reg_resident_ctas(int device, int grid_capacity) {

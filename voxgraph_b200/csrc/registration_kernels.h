@@ -25,7 +25,7 @@ struct RegPoseConst;
 #define VGX_REG_SKIPGRAM 1         // no Gram stage for a unit without a single correspondence
 #endif
 #ifndef VGX_REG_HW_TILE_UNITS
-#define VGX_REG_HW_TILE_UNITS 32   // > 0: one CTA per tile of that many units (hardware scheduling); 0: persistent
+#define VGX_REG_HW_TILE_UNITS 64   // > 0: one CTA per tile of that many units (hardware scheduling); 0: persistent
 #endif
 #define VGX_REG_UNIT 32            // points per unit = one warp iteration; tiles are cut on unit boundaries
 #ifndef VGX_REG_STREAM_OCTETS
@@ -45,12 +45,14 @@ struct __align__(16) RegTile {   // 32 bytes: everything a CTA needs to start it
 
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
                                RegPoseConst* poses, int n);
-// Persistent CTAs walk their tiles -> partial sums -> (last tile of each constraint)
-// per-constraint sums csum[c][21].
+// One CTA per tile (or persistent CTAs walking their tiles) -> partials[tile][21]; the consumer adds
+// a constraint's tiles in tile order (graph.cu: reg_constraint_sum).
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
                            const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
-                           const int* tile_begin, int* counters, double* partials, double* csum,
-                           int grid_capacity, bool jacobian);
+                           const int* tile_order, int* tile_cost, double* partials, int grid_capacity,
+                           bool jacobian);
+// tile_order <- tiles sorted by measured cost, most expensive first (one-CTA-per-tile mode)
+void vgx_launch_reg_order(cudaStream_t st, const int* tile_cost, int n_tiles, int* tile_order);
 // persistent grid size: SMs x CTAs that are co-resident with `grid_capacity` cells of dynamic smem
 int vgx_reg_resident_ctas(int device, int grid_capacity);
 // Fills the descriptor of one (reference -> reading) residual block.  Deterministic mode: pts / n /
