@@ -277,6 +277,7 @@ def stream_leg(ctx, api, st, voxel_size, scans_per_submap, peak, cpu_scans=3):
                               "pairs_last": switch[-1]["pairs"] if switch else 0,
                               "isosurface_points_last": switch[-1].get("isosurface_points") if switch else None,
                               "blocks_last": switch[-1].get("finished_blocks") if switch else None},
+            "switch_timings_ms": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()} for t in m.timings],
             "submap_origin_xy_error_odometry_m": err_odo, "submap_origin_xy_error_optimised_m": err_opt,
             "submap_origin_xy_error_optimised_tight_m": err_opt_tight, "lm_iterations_tight": tight_iters,
             "cpu_reference_integrate_ms_per_scan_mt": float(np.median(cpu_ms)), "cpu_reference_threads": nt,

@@ -91,6 +91,12 @@ struct VgxGraph {
   double* d_step = nullptr;
   LmState* d_state = nullptr;
   LmState* h_state = nullptr;
+  LmState* d_snap = nullptr;    // [2] outcome of iteration k (written by lm_decide), parity k & 1
+  LmState* h_snap = nullptr;    // [2] pinned
+  double* h_x = nullptr;        // pinned, 4 * h_x_cap
+  int h_x_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_iter[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
   float* d_sample_pts = nullptr;   // gathered unit-major points of the local sampled blocks
   int32_t* d_sample_idx = nullptr;
 };
@@ -107,19 +113,28 @@ static void free_tables(VgxGraph* g) {
   cudaFree(g->d_state);
   cudaFree(g->d_sample_pts); cudaFree(g->d_sample_idx);
   g->d_sample_pts = nullptr; g->d_sample_idx = nullptr;
-  if (g->h_state) cudaFreeHost(g->h_state);
+  cudaFree(g->d_snap); g->d_snap = nullptr;
+  // the pinned host buffers (h_state, h_snap, h_x) outlive the tables: cudaMallocHost costs ~0.2 ms each
   g->d_cons = nullptr; g->d_poses = nullptr; g->d_tiles = nullptr; g->d_tile_begin = nullptr; g->d_cta_tile_begin = nullptr;
   g->d_partials = nullptr; g->d_csum = nullptr; g->d_rel = nullptr; g->d_counters = nullptr;
   g->d_csr_begin = nullptr; g->d_csr_items = nullptr; g->d_block_nodes = nullptr;
   g->d_red_offset = nullptr; g->d_x = nullptr; g->d_xc = nullptr;
   g->d_packed[0] = g->d_packed[1] = nullptr;
   g->d_A = nullptr; g->d_scale = nullptr; g->d_diag = nullptr; g->d_gs = nullptr; g->d_step = nullptr;
-  g->d_state = nullptr; g->h_state = nullptr;
+  g->d_state = nullptr;
 }
 
 void vgx_graph_free(vgx_ctx* c) {
   if (!c->graph) return;
+  cudaStreamSynchronize(c->stream);
   free_tables(c->graph);
+  if (c->graph->h_state) cudaFreeHost(c->graph->h_state);
+  if (c->graph->h_snap) cudaFreeHost(c->graph->h_snap);
+  if (c->graph->h_x) cudaFreeHost(c->graph->h_x);
+  if (c->graph->copy_stream) {
+    cudaStreamDestroy(c->graph->copy_stream);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->graph->ev_iter[k]); cudaEventDestroy(c->graph->ev_copy[k]); }
+  }
   delete c->graph;
   c->graph = nullptr;
 }
@@ -380,9 +395,10 @@ __global__ void __launch_bounds__(128)
 assemble_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
                 const int4* __restrict__ items, VgxP2PPush push, int N, int E, int n_reg,
-                int n_rel, int exclude_reg, VgxP2PSignal sig) {
+                int n_rel, int exclude_reg, VgxP2PSignal sig, const int* __restrict__ skip) {
   __shared__ double s_part[4][20];
   __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
+  if (skip && *skip) return;   // evaluation enqueued ahead of a solve that has already ended
   // programmatic dependent of the reduce kernel: scheduled while that grid drains, blocked here until
   // it has completed and its tile sums are visible
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -402,7 +418,8 @@ assemble_exchange_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
                          const double* __restrict__ x, const int* __restrict__ csr_begin,
                          const int4* __restrict__ items, VgxP2PPush push, int N, int E,
                          int n_reg, int n_rel, int exclude_reg, VgxP2PSignal sig, VgxP2PGather gat,
-                         double* __restrict__ out, int count) {
+                         double* __restrict__ out, int count, const int* __restrict__ skip) {
+  if (skip && *skip) return;   // identical on every rank (the ranks' solver states are bit-identical)
   __shared__ double s_part[4][20];
   __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
   __shared__ int s_ok;
@@ -433,6 +450,7 @@ __global__ void lm_build_kernel(const double* __restrict__ packed, const int* __
                                 double* __restrict__ A, double* __restrict__ scale,
                                 double* __restrict__ diag, double* __restrict__ gs,
                                 LmState* __restrict__ st, LmOpts o) {
+  if (st->done) return;   // an iteration enqueued ahead of the host's look at the previous one
   const int M = n + 1;
   const double* g = packed + PACK_HDR;
   const double* D = packed + PACK_HDR + 4 * (size_t)N;
@@ -492,6 +510,7 @@ __global__ void lm_build_kernel(const double* __restrict__ packed, const int* __
 __global__ void lm_persist_kernel(const double* __restrict__ packed, const int* __restrict__ red,
                                   int N, double* __restrict__ scale, double* __restrict__ diag,
                                   LmState* __restrict__ st, LmOpts o) {
+  if (st->done) return;
   const double* D = packed + PACK_HDR + 4 * (size_t)N;
   const bool first = st->scale_ready == 0;
   const bool reuse = st->reuse_diagonal != 0;
@@ -528,6 +547,7 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 __global__ void __launch_bounds__(1024) chol_kernel(double* __restrict__ A, int n,
                                                     LmState* __restrict__ st) {
   extern __shared__ double smem[];
+  if (st->done) return;
   double* sD = smem;                 // 32 x 33
   double* sP = smem + CH_NB * 33;    // rows x 33
   const int M = n + 1;
@@ -624,11 +644,12 @@ __device__ __forceinline__ void dmma_sub_8x8x4(double& c0, double& c1, double a,
 // m8n8k4 FP64 MMAs (warps over 8-row tiles), (2) warp 0 factors the 8x8 diagonal block,
 // (3) one thread per row solves the panel.  Then back substitution in place.
 #define CS_NB 8
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__ xsol,
                        LmState* __restrict__ st) {
   extern __shared__ double S[];  // packed columns: column j holds rows j..n
   __shared__ int s_fail;
+  if (st->done) return;
   const int M = n + 1;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -648,14 +669,32 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
         const int i0 = J0 + 8 * tile;
         const int ra = i0 + g;        // row of this lane's A fragment element
         const int rb = J0 + g;        // row (= column of the block) of its B fragment element
-        double c0 = 0.0, c1 = 0.0;
-        for (int k0 = 0; k0 < J0; k0 += 4) {
-          const int kc = k0 + t;      // J0 is a multiple of 8, so kc < J0
+        // four independent accumulator pairs: the k-loop is a chain of dependent MMAs otherwise
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0 = 0.0, h1 = 0.0;
+        const bool va = ra < M, vb = rb < n;
+        int k0 = 0;
+        for (; k0 + 16 <= J0; k0 += 16) {
+          const int kc = k0 + t;      // J0 is a multiple of 8, so every kc below is < J0
+          const int o0 = tri_off(kc, M) - kc, o1 = tri_off(kc + 4, M) - (kc + 4),
+                    o2 = tri_off(kc + 8, M) - (kc + 8), o3 = tri_off(kc + 12, M) - (kc + 12);
+          const double a0 = va ? S[o0 + ra] : 0.0, b0 = vb ? S[o0 + rb] : 0.0;
+          const double a1 = va ? S[o1 + ra] : 0.0, b1 = vb ? S[o1 + rb] : 0.0;
+          const double a2 = va ? S[o2 + ra] : 0.0, b2 = vb ? S[o2 + rb] : 0.0;
+          const double a3 = va ? S[o3 + ra] : 0.0, b3 = vb ? S[o3 + rb] : 0.0;
+          dmma_sub_8x8x4(c0, c1, a0, b0);
+          dmma_sub_8x8x4(e0, e1, a1, b1);
+          dmma_sub_8x8x4(f0, f1, a2, b2);
+          dmma_sub_8x8x4(h0, h1, a3, b3);
+        }
+        for (; k0 < J0; k0 += 4) {
+          const int kc = k0 + t;
           const int ok = tri_off(kc, M) - kc;
-          const double a = (ra < M) ? S[ok + ra] : 0.0;
-          const double b = (rb < n) ? S[ok + rb] : 0.0;
+          const double a = va ? S[ok + ra] : 0.0;
+          const double b = vb ? S[ok + rb] : 0.0;
           dmma_sub_8x8x4(c0, c1, a, b);
         }
+        c0 = (c0 + e0) + (f0 + h0);
+        c1 = (c1 + e1) + (f1 + h1);
         // lane holds C[g][2t], C[g][2t+1] -> element (row i0+g, col J0+2t(+1)), lower part only
         const int r = i0 + g;
         if (r < M) {
@@ -694,55 +733,67 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
         if (lane < nb && c <= lane && c < nb) S[tri_off(J0 + c, M) + lane - c] = row[c];
     }
     __syncthreads();
-    // (3) panel solve: rows below the block (incl. the rhs row n)
+    // (3) panel solve: rows below the block (incl. the rhs row n).  The 8x8 block and the row's eight
+    //     entries are loaded first, so the substitution chain runs on registers only.
     for (int r = J0 + nb + tid; r < M; r += T) {
-      double x[CS_NB];
+      double x[CS_NB], Lb[CS_NB][CS_NB];
+#pragma unroll
+      for (int c = 0; c < CS_NB; ++c) {
+        x[c] = (c < nb) ? S[tri_off(J0 + c, M) + r - (J0 + c)] : 0.0;
+#pragma unroll
+        for (int k = 0; k < CS_NB; ++k) Lb[c][k] = (k < c && c < nb) ? S[tri_off(J0 + k, M) + c - k] : 0.0;
+      }
 #pragma unroll
       for (int c = 0; c < CS_NB; ++c) {
         if (c < nb) {
-          const int oc = tri_off(J0 + c, M);
-          double v = S[oc + r - (J0 + c)];
+          double v = x[c];
 #pragma unroll
           for (int k = 0; k < CS_NB; ++k)
-            if (k < c) v -= x[k] * S[tri_off(J0 + k, M) + c - k];
-          v *= rinv[J0 + c];
-          x[c] = v;
-          S[oc + r - (J0 + c)] = v;
+            if (k < c) v -= x[k] * Lb[c][k];
+          x[c] = v * rinv[J0 + c];
         }
       }
-    }
-    __syncthreads();
-  }
-  // back substitution L^T x = y (y = row n of L, kept in place as element n of each column),
-  // blocked by 8: warp 0 solves the 8 unknowns of a block, then every thread folds them into
-  // the remaining right-hand side with 8 FMAs.
-  for (int J0 = ((n - 1) / CS_NB) * CS_NB; J0 >= 0; J0 -= CS_NB) {
-    const int nb = min(CS_NB, n - J0);
-    if (warp == 0) {
-      for (int k = nb - 1; k >= 0; --k) {
-        const int ok = tri_off(J0 + k, M);
-        const double xk = S[ok + n - (J0 + k)] * rinv[J0 + k];
-        __syncwarp();
-        if (lane == 0) S[ok + n - (J0 + k)] = xk;
-        if (lane < k) {
-          const int oi = tri_off(J0 + lane, M);
-          S[oi + n - (J0 + lane)] = fma(-S[oi + k - lane], xk, S[oi + n - (J0 + lane)]);
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < J0; i += T) {
-      const int oi = tri_off(i, M);
-      double y = S[oi + n - i];
 #pragma unroll
-      for (int k = 0; k < CS_NB; ++k)
-        if (k < nb) y = fma(-S[oi + (J0 + k) - i], S[tri_off(J0 + k, M) + n - (J0 + k)], y);
-      S[oi + n - i] = y;
+      for (int c = 0; c < CS_NB; ++c)
+        if (c < nb) S[tri_off(J0 + c, M) + r - (J0 + c)] = x[c];
     }
     __syncthreads();
   }
-  for (int k = tid; k < n; k += T) xsol[k] = S[tri_off(k, M) + n - k];
+  // back substitution L^T x = y (y = row n of L, element n of each column): ONE warp, y in
+  // registers (lane l owns unknowns l, l + 32, ...).  Step j: the owner scales its y_j, one shuffle
+  // broadcasts x_j, every lane folds it into its remaining unknowns with loads that do not depend
+  // on the chain - n steps of (FMA, MUL, SHFL) instead of n/8 block steps with barriers.
+  constexpr int kSlots = 8;   // n <= 256 (the shared-memory variant holds ~230 unknowns)
+  if (warp == 0) {
+    double y[kSlots];
+    int base[kSlots];
+#pragma unroll
+    for (int m = 0; m < kSlots; ++m) {
+      const int i = lane + 32 * m;
+      base[m] = i < n ? tri_off(i, M) - i : 0;
+      y[m] = i < n ? S[base[m] + n] : 0.0;
+    }
+#pragma unroll
+    for (int m = kSlots - 1; m >= 0; --m) {
+      if (32 * m < n) {   // warp-uniform
+        for (int l = min(31, n - 1 - 32 * m); l >= 0; --l) {
+          const int j = 32 * m + l;
+          const double xj = __shfl_sync(0xffffffffu, y[m] * rinv[j], l);
+          if (lane == l) y[m] = xj;
+#pragma unroll
+          for (int mm = 0; mm <= m; ++mm) {
+            const int i = lane + 32 * mm;
+            if (i < j) y[mm] = fma(-S[base[mm] + j], xj, y[mm]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < kSlots; ++m) {
+      const int i = lane + 32 * m;
+      if (i < n) xsol[i] = y[m];
+    }
+  }
   if (tid == 0 && s_fail) st->step_valid = 0;
 }
 
@@ -752,6 +803,7 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
 __global__ void __launch_bounds__(256) chol_coop_kernel(double* __restrict__ A, int n,
                                                         LmState* __restrict__ st) {
   cg::grid_group grid = cg::this_grid();
+  if (st->done) return;   // uniform over the grid
   __shared__ double sD[CH_NB * 33];
   __shared__ double sPi[CH_NB * 33];
   __shared__ double sPj[CH_NB * 33];
@@ -860,6 +912,7 @@ lm_step_kernel(const double* __restrict__ A, int n, int N, const int* __restrict
                const double* __restrict__ presolved) {
   extern __shared__ double sy[];  // n
   __shared__ double s_red[3][32];
+  if (st->done) return;
   const int M = n + 1;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   for (int i = tid; i < n; i += T) sy[i] = presolved ? presolved[i] : A[(size_t)i * M + n];
@@ -941,8 +994,12 @@ __global__ void lm_decide_kernel(const double* __restrict__ packed_cur,
                                  const double* __restrict__ packed_cand,
                                  const int* __restrict__ red, int N, double* __restrict__ x,
                                  const double* __restrict__ xc, LmState* __restrict__ st, LmOpts o,
-                                 int cand_eval_ok) {
+                                 int cand_eval_ok, LmState* __restrict__ snapshot) {
   __shared__ double s_g[32];
+  if (st->done) {   // no-op iteration: the snapshot still tells the host the solve has ended
+    if (threadIdx.x == 0) *snapshot = *st;
+    return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // gradient max norm at the candidate (used if accepted)
   double gm = 0;
@@ -1002,10 +1059,20 @@ __global__ void lm_decide_kernel(const double* __restrict__ packed_cur,
     S.step_valid = 1;
     s_accept = S.accepted;
     *st = S;
+    *snapshot = S;   // what the host reads (the live state is rewritten by the next iteration's kernels)
   }
   __syncthreads();
   if (s_accept)
     for (int t = tid; t < 4 * N; t += blockDim.x) x[t] = xc[t];
+}
+
+// The candidate's normal equations become the current ones when the step was accepted (slot 1 ->
+// slot 0), so every kernel of an iteration has fixed arguments whatever the decisions were.
+__global__ void lm_accept_kernel(const double* __restrict__ cand, double* __restrict__ cur, size_t len,
+                                 const LmState* __restrict__ st) {
+  if (!st->accepted) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
+    cur[i] = cand[i];
 }
 
 __global__ void lm_init_kernel(const double* __restrict__ packed, const int* __restrict__ red, int N,
@@ -1302,7 +1369,23 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   dmalloc((void**)&g->d_gs, sizeof(double) * n);
   dmalloc((void**)&g->d_step, sizeof(double) * n);
   dmalloc((void**)&g->d_state, sizeof(LmState));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&g->h_state, sizeof(LmState));
+  if (e == cudaSuccess && !g->h_state) e = cudaMallocHost((void**)&g->h_state, sizeof(LmState));
+  dmalloc((void**)&g->d_snap, 2 * sizeof(LmState));
+  if (e == cudaSuccess && !g->h_snap) e = cudaMallocHost((void**)&g->h_snap, 2 * sizeof(LmState));
+  if (e == cudaSuccess && g->h_x_cap < N) {
+    if (g->h_x) cudaFreeHost(g->h_x);
+    g->h_x = nullptr;
+    g->h_x_cap = std::max(2 * N, 64);
+    e = cudaMallocHost((void**)&g->h_x, sizeof(double) * 4 * (size_t)g->h_x_cap);
+    if (e != cudaSuccess) g->h_x_cap = 0;
+  }
+  if (e == cudaSuccess && !g->copy_stream) {
+    e = cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaEventCreateWithFlags(&g->ev_iter[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_copy[k], cudaEventDisableTiming);
+    }
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     free_tables(g);
@@ -1315,7 +1398,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
 
 // ------------------------------------------------------------------ evaluation pipeline
 static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_packed, bool jacobian,
-                        bool exclude_reg) {
+                        bool exclude_reg, const int* skip = nullptr) {
   cudaStream_t st = c->stream;
   const bool do_reg = !exclude_reg && g->n_local > 0;
   if (do_reg) {
@@ -1329,12 +1412,12 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     if (g->evals_since_order >= 0) ++g->evals_since_order;
     {
       VgxLaunchScope s(c, 5);
-      vgx_launch_reg_pose_setup(st, g->d_cons, d_x, g->d_poses, g->n_local);
+      vgx_launch_reg_pose_setup(st, g->d_cons, d_x, g->d_poses, g->n_local, skip);
     }
     {
       VgxLaunchScope s(c, 0);
       vgx_launch_reg_reduce(st, g->d_cons, g->d_poses, g->d_tiles, g->n_ctas, g->d_cta_tile_begin,
-                            g->d_tile_order, g->d_tile_cost, g->d_partials, g->grid_capacity, jacobian);
+                            g->d_tile_order, g->d_tile_cost, g->d_partials, g->grid_capacity, jacobian, skip);
     }
     if (g->evals_since_order < 0) g->evals_since_order = -2;   // a cost has been measured now
   }
@@ -1382,7 +1465,7 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
       cfg.gridDim = dim3((unsigned)grid);
       cudaLaunchKernelEx(&cfg, assemble_exchange_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x,
                          (const int*)g->d_csr_begin, (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local,
-                         g->n_rel_local, excl, sig, gat, d_packed, (int)g->packed_len);
+                         g->n_rel_local, excl, sig, gat, d_packed, (int)g->packed_len, skip);
     }
     VGX_CUDA(c, cudaGetLastError());
     return VGX_OK;
@@ -1391,7 +1474,7 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     VgxLaunchScope s(c, 5);
     cfg.gridDim = dim3((unsigned)(g->N + g->E + 1));
     cudaLaunchKernelEx(&cfg, assemble_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x, (const int*)g->d_csr_begin,
-                       (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, sig);
+                       (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, sig, skip);
   }
   VGX_CUDA(c, cudaGetLastError());
   if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len);
@@ -1854,7 +1937,7 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
   // dense Cholesky: whole system in shared memory when it fits (configs[0..1]), else the
   // cooperative multi-CTA kernel, else one CTA streaming from global memory
   const size_t smem_chol_bytes = sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + n + 2);
-  const bool use_smem_chol = n > 0 && smem_chol_bytes <= 220 * 1024;
+  const bool use_smem_chol = n > 0 && n <= 256 && smem_chol_bytes <= 220 * 1024;
   if (use_smem_chol)
     VGX_CUDA(c, cudaFuncSetAttribute(chol_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_chol_bytes));
@@ -1888,32 +1971,39 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
   lo.max_lm_diagonal = o->max_lm_diagonal;
   lo.jacobi_scaling = o->jacobi_scaling;
 
-  int cur = 0;
-  rc = eval_enqueue(c, g, g->d_x, g->d_packed[cur], true, excl);
+  // Slot 0 of d_packed always holds the normal equations at the current poses, slot 1 the candidate's;
+  // an accepted step copies 1 -> 0 on the device, so an iteration is a fixed sequence of launches
+  // that needs nothing from the host.  The host therefore runs ONE ITERATION AHEAD: iteration k + 1
+  // is enqueued before the 144-byte outcome of iteration k has been read (on a second stream, from
+  // a snapshot the decide kernel writes); every kernel of an iteration returns at once when the
+  // solve has ended, so the speculative iteration after the last one is a row of empty launches
+  // that drain while the host already returns.  Multi-rank: no run-ahead (the ranks stay in step).
+  rc = eval_enqueue(c, g, g->d_x, g->d_packed[0], true, excl);
   if (rc != VGX_OK) return rc;
   {
     VgxLaunchScope s(c, 4);
-    lm_init_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_red_offset, N, g->d_state,
+    lm_init_kernel<<<1, 256, 0, st>>>(g->d_packed[0], g->d_red_offset, N, g->d_state,
                                       o->initial_trust_region_radius, lo);
   }
   VGX_CUDA(c, cudaMemcpyAsync(g->h_state, g->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
   VGX_CUDA(c, cudaStreamSynchronize(st));
   S.initial_cost = g->h_state->cost;
   bool timed_out = false;
-  while (!g->h_state->done && n > 0) {
-    // (single-rank only: ranks must take identical decisions or the all-reduce would hang)
-    if (c->nranks == 1 && wall_s() - t0 >= o->max_solver_time_s) { timed_out = true; break; }
+  static const char* no_spec = getenv("VGX_LM_NO_RUNAHEAD");
+  const int ahead = (c->nranks == 1 && !(no_spec && no_spec[0] == '1')) ? 1 : 0;
+  const int* skip = &g->d_state->done;
+  auto enqueue_iteration = [&](int k) -> int {
     {
       VgxLaunchScope s(c, 4, 4);
       VGX_CUDA(c, cudaMemsetAsync(g->d_A, 0, sizeof(double) * (size_t)(n + 1) * (n + 1), st));
       const int nthreads = std::max(16 * (N + g->E), 4 * N);
       lm_build_kernel<<<std::min(296, (nthreads + 255) / 256), 256, 0, st>>>(
-          g->d_packed[cur], g->d_red_offset, g->d_block_nodes, N, g->E, n, g->d_A, g->d_scale, g->d_diag,
+          g->d_packed[0], g->d_red_offset, g->d_block_nodes, N, g->E, n, g->d_A, g->d_scale, g->d_diag,
           g->d_gs, g->d_state, lo);
-      lm_persist_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_red_offset, N, g->d_scale, g->d_diag,
+      lm_persist_kernel<<<1, 256, 0, st>>>(g->d_packed[0], g->d_red_offset, N, g->d_scale, g->d_diag,
                                            g->d_state, lo);
       if (use_smem_chol) {
-        chol_solve_smem_kernel<<<1, 1024, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state);
+        chol_solve_smem_kernel<<<1, 512, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state);
       } else if (coop_grid > 0) {
         int n_arg = n;
         void* args[] = {(void*)&g->d_A, (void*)&n_arg, (void*)&g->d_state};
@@ -1927,21 +2017,57 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
     }
     VGX_CUDA(c, cudaGetLastError());
     // candidate evaluated with Jacobians so an accepted step needs no second pass
-    rc = eval_enqueue(c, g, g->d_xc, g->d_packed[1 - cur], true, excl);
-    if (rc != VGX_OK) return rc;
+    int rc2 = eval_enqueue(c, g, g->d_xc, g->d_packed[1], true, excl, skip);
+    if (rc2 != VGX_OK) return rc2;
     {
-      VgxLaunchScope s(c, 4);
-      lm_decide_kernel<<<1, 256, 0, st>>>(g->d_packed[cur], g->d_packed[1 - cur], g->d_red_offset, N,
-                                          g->d_x, g->d_xc, g->d_state, lo, 1);
+      VgxLaunchScope s(c, 4, 2);
+      lm_decide_kernel<<<1, 256, 0, st>>>(g->d_packed[0], g->d_packed[1], g->d_red_offset, N, g->d_x,
+                                          g->d_xc, g->d_state, lo, 1, g->d_snap + (k & 1));
+      lm_accept_kernel<<<std::max(1, std::min(64, (int)(g->packed_len / 2048))), 256, 0, st>>>(
+          g->d_packed[1], g->d_packed[0], g->packed_len, g->d_state);
     }
-    VGX_CUDA(c, cudaMemcpyAsync(g->h_state, g->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+    VGX_CUDA(c, cudaGetLastError());
+    // outcome of iteration k -> host, on the copy stream (the main stream keeps running ahead)
+    VGX_CUDA(c, cudaEventRecord(g->ev_iter[k & 1], st));
+    VGX_CUDA(c, cudaStreamWaitEvent(g->copy_stream, g->ev_iter[k & 1], 0));
+    VGX_CUDA(c, cudaMemcpyAsync(g->h_snap + (k & 1), g->d_snap + (k & 1), sizeof(LmState),
+                                cudaMemcpyDeviceToHost, g->copy_stream));
+    VGX_CUDA(c, cudaEventRecord(g->ev_copy[k & 1], g->copy_stream));
+    return VGX_OK;
+  };
+  bool run = !g->h_state->done && n > 0;
+  if (run) {
+    int enq = 0, k = 0;   // iterations enqueued / the one whose outcome is awaited
+    for (;;) {
+      while (enq <= k + ahead) {
+        // (single-rank only: ranks must take identical decisions or the exchange would hang)
+        if (enq > k && c->nranks == 1 && wall_s() - t0 >= o->max_solver_time_s) break;
+        rc = enqueue_iteration(enq);
+        if (rc != VGX_OK) return rc;
+        ++enq;
+      }
+      VGX_CUDA(c, cudaEventSynchronize(g->ev_copy[k & 1]));
+      *g->h_state = g->h_snap[k & 1];
+      if (g->h_state->done) break;
+      if (c->nranks == 1 && wall_s() - t0 >= o->max_solver_time_s) { timed_out = true; break; }
+      ++k;
+    }
+    if (timed_out) VGX_CUDA(c, cudaStreamSynchronize(st));   // iterations in flight still move x
+    // final poses: the main stream may still be draining the empty launches of the speculative
+    // iteration; the copy stream is ordered after the deciding iteration only
+    VGX_CUDA(c, cudaMemcpyAsync(g->h_x, g->d_x, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost,
+                                timed_out ? st : g->copy_stream));
+    VGX_CUDA(c, cudaStreamSynchronize(timed_out ? st : g->copy_stream));
+    if (timed_out) {
+      VGX_CUDA(c, cudaMemcpyAsync(g->h_state, g->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+      VGX_CUDA(c, cudaStreamSynchronize(st));
+    }
+    memcpy(g->x.data(), g->h_x, sizeof(double) * 4 * N);
+  } else {
+    VGX_CUDA(c, cudaMemcpyAsync(g->x.data(), g->d_x, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, st));
     VGX_CUDA(c, cudaStreamSynchronize(st));
-    if (g->h_state->accepted) cur = 1 - cur;
   }
   if (n == 0) { g->h_state->termination = 2; }
-  // keep the packed result of the current poses in slot 0 for later vgx_graph_eval users
-  VGX_CUDA(c, cudaMemcpyAsync(g->x.data(), g->d_x, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, st));
-  VGX_CUDA(c, cudaStreamSynchronize(st));
   S.iterations = g->h_state->iterations;
   S.num_successful_steps = g->h_state->successful;
   S.num_residual_evals = g->h_state->evals;

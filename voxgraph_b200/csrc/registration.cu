@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(VGX_REG_THREADS, VGX_REG_MIN_BLOCKS)
 reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
                   const RegPoseConst* __restrict__ poses, const RegTile* __restrict__ tiles,
                   const int* __restrict__ cta_tile_begin, const int* __restrict__ tile_order,
-                  int* __restrict__ tile_cost, double* __restrict__ partials, int grid_capacity) {
+                  int* __restrict__ tile_cost, double* __restrict__ partials, int grid_capacity,
+                  const int* __restrict__ skip) {
+  if (skip && *skip) return;   // evaluation enqueued ahead of a solve that has already ended
   constexpr int kWarps = VGX_REG_THREADS / 32;
   constexpr int kRing = VGX_REG_RING;
   __shared__ __align__(128) float s_ring[kWarps][kRing][5][32];
@@ -367,7 +369,7 @@ void vgx_launch_reg_order(cudaStream_t st, const int* tile_cost, int n_tiles, in
 
 __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ constraints,
                                       const double* __restrict__ x, RegPoseConst* __restrict__ poses,
-                                      int n_constraints) {
+                                      int n_constraints, const int* __restrict__ skip) {
   // programmatic dependent launch: the reduce kernel may start its prologue (tile records, TMA of the
   // descriptors, block grids and first point units) while the pose blocks are still being computed
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -375,6 +377,7 @@ __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ const
   // still running: the pose blocks it overwrites were read by that evaluation's reduce kernel, which
   // has completed once the assembly (its dependent) has
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (skip && *skip) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_constraints) return;
   RegPoseConst P;
@@ -384,7 +387,7 @@ __global__ void reg_pose_setup_kernel(const RegConstraintDev* __restrict__ const
 
 // ------------------------------------------------------------------ launch helpers
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
-                               RegPoseConst* poses, int n) {
+                               RegPoseConst* poses, int n, const int* skip) {
   if (n <= 0) return;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -397,13 +400,13 @@ void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, co
   static const char* no_pdl = getenv("VGX_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
-  cudaLaunchKernelEx(&cfg, reg_pose_setup_kernel, cons, x, poses, n);
+  cudaLaunchKernelEx(&cfg, reg_pose_setup_kernel, cons, x, poses, n, skip);
 }
 
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
                            const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
                            const int* tile_order, int* tile_cost, double* partials, int grid_capacity,
-                           bool jacobian) {
+                           bool jacobian, const int* skip) {
   if (n_ctas <= 0) return;
   // launched with programmatic stream serialisation: its CTAs may start while the pose set-up kernel
   // is still running; they block at griddepcontrol.wait before touching the pose blocks
@@ -421,10 +424,10 @@ void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const 
   cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   if (jacobian)
     cudaLaunchKernelEx(&cfg, reg_reduce_kernel<true>, cons, poses, tiles, cta_tile_begin, tile_order, tile_cost,
-                       partials, grid_capacity);
+                       partials, grid_capacity, skip);
   else
     cudaLaunchKernelEx(&cfg, reg_reduce_kernel<false>, cons, poses, tiles, cta_tile_begin, tile_order, tile_cost,
-                       partials, grid_capacity);
+                       partials, grid_capacity, skip);
 }
 
 int vgx_reg_resident_ctas(int device, int grid_capacity) {

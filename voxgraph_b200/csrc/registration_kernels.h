@@ -43,14 +43,16 @@ struct __align__(16) RegTile {   // 32 bytes: everything a CTA needs to start it
   const uint16_t* grid16;
 };
 
+// skip (device flag, may be null): when set, the kernel returns at once (an evaluation enqueued
+// ahead of a solve that has ended in the meantime)
 void vgx_launch_reg_pose_setup(cudaStream_t st, const RegConstraintDev* cons, const double* x,
-                               RegPoseConst* poses, int n);
+                               RegPoseConst* poses, int n, const int* skip = nullptr);
 // One CTA per tile (or persistent CTAs walking their tiles) -> partials[tile][21]; the consumer adds
 // a constraint's tiles in tile order (graph.cu: reg_constraint_sum).
 void vgx_launch_reg_reduce(cudaStream_t st, const RegConstraintDev* cons, const RegPoseConst* poses,
                            const RegTile* tiles, int n_ctas, const int* cta_tile_begin,
                            const int* tile_order, int* tile_cost, double* partials, int grid_capacity,
-                           bool jacobian);
+                           bool jacobian, const int* skip = nullptr);
 // tile_order <- tiles sorted by measured cost, most expensive first (one-CTA-per-tile mode)
 void vgx_launch_reg_order(cudaStream_t st, const int* tile_cost, int n_tiles, int* tile_order);
 // persistent grid size: SMs x CTAs that are co-resident with `grid_capacity` cells of dynamic smem

@@ -106,9 +106,13 @@ class VoxgraphMapper:
         ctx = self.ctx
         if not self.empty():
             t0 = time.time()
-            ctx.submap_finish_ex(self.active_id, self.filter)          # finishSubmap()
+            ctx.submap_finish(self.active_id)                          # finishSubmap(): registration view + grid
+            ctx.synchronize()
+            t1 = time.time()
+            ctx.submap_extract_points(self.active_id, self.filter)    # ... registration points, OBB, isosurface blocks
             ctx.synchronize()
             rec["finish_ms"] = (time.time() - t0) * 1e3
+            rec["view_ms"] = (t1 - t0) * 1e3
             rec["finished_blocks"] = ctx.submap_block_count(self.active_id)
             rec["isosurface_points"] = ctx.submap_num_points(self.active_id, api.K_ISOSURFACE_POINTS)
         if self.cfg.registration_constraints_enabled and len(self.submap_ids) >= 2:
