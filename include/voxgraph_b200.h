@@ -48,7 +48,8 @@ int vgx_ctx_synchronize(vgx_ctx* ctx);
 /* Kernel accounting: when enabled the library brackets each of its kernels with
  * CUDA events on the context stream. which: 0 = registration reduce kernel,
  * 1 = registration emit kernel, 2 = TSDF integrate kernel, 3 = TSDF allocate kernel,
- * 4 = Cholesky/LM kernels, 5 = everything else. */
+ * 4 = Cholesky/LM kernels, 5 = everything else, 6 = registration pose set-up, 7 = per-constraint sums,
+ * 8 = assembly of the normal equations (+ the peer exchange when it is fused into it). */
 int vgx_profile_enable(vgx_ctx* ctx, int on);
 int vgx_profile_reset(vgx_ctx* ctx);
 int vgx_profile_get(vgx_ctx* ctx, int which, double* total_ms, int64_t* launches);

@@ -222,8 +222,14 @@ __device__ __forceinline__ double reg_constraint_sum(const RegSums& R, int c, in
   return reg_tile_sum(R.partials, R.tile_begin[c], R.tile_begin[c + 1], e) * (f * f);
 }
 
-// per-constraint sums for the host (vgx_graph_registration_costs): one warp per constraint
-__global__ void reg_csum_kernel(RegSums R, int n, double* __restrict__ csum) {
+// Per-constraint sums csum[c][21] from the tile rows: one warp per constraint, a programmatic
+// dependent of the reduce kernel (and the assembly kernel is one of this).  A separate, massively
+// parallel stage: inside the assembly the same loop is a chain of dependent L2 latencies per item.
+__global__ void __launch_bounds__(128)
+reg_csum_kernel(RegSums R, int n, double* __restrict__ csum, const int* __restrict__ skip) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (skip && *skip) return;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c < n && lane < VGX_REG_NSUM) csum[(size_t)c * VGX_REG_NSTRIDE + lane] = reg_constraint_sum(R, c, lane);
 }
@@ -235,60 +241,22 @@ __global__ void reg_csum_kernel(RegSums R, int n, double* __restrict__ csum) {
 // je[0..2] == -jr[0..2]; a relative-pose item is evaluated on the fly.
 // item = (source, role): source >= 0 registration constraint, < 0 relative edge -(e+1);
 // role 0: A-A, 1: B-B, 2: rows A / cols B, 3: rows B / cols A.
-// Multi-rank peer exchange: the last CTA of the assembly to finish publishes this rank's
-// partial to every peer (system-scope fence, then one flag store per rank over NVLink).
-__device__ __forceinline__ void assemble_signal(const VgxP2PSignal& sig) {
-  if (sig.nranks == 0) return;
-  __shared__ int s_sig_last;
-  __threadfence_system();   // this CTA's pushed values are visible to the peers before its ticket counts
-  __syncthreads();
-  if (threadIdx.x == 0) s_sig_last = (atomicAdd(sig.counter, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (s_sig_last) {
-    __threadfence_system();
-    if (threadIdx.x < sig.nranks) {
-      volatile unsigned long long* f = sig.flags[threadIdx.x] + sig.rank;
-      *f = sig.epoch;
-    }
-    if (threadIdx.x == 0) *sig.counter = 0;
-    __threadfence_system();
-  }
-}
-
 // Work of one output block `ob` (N diagonal, E off-diagonal, ob == N + E: the cost) by one
 // 4-warp CTA: warp w sums items w, w+4, ...; the four partial sums are combined in warp order
 // -> bit-reproducible. Ends with a __syncthreads() so it can be called in a loop.
-#define VGX_ASM_CHUNK 24   // items whose constraint sums are staged in shared memory at a time
-__device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
+__device__ __forceinline__ void assemble_block(int ob, const double* __restrict__ csum,
                                                const VgxRelEdge* __restrict__ rel,
                                                const double* __restrict__ x,
                                                const int* __restrict__ csr_begin,
                                                const int4* __restrict__ items,
                                                const VgxP2PPush& push, int N, int E, int n_reg,
-                                               int n_rel, int exclude_reg, double (*s_part)[20],
-                                               double (*s_sums)[VGX_REG_NSUM]) {
+                                               int n_rel, int exclude_reg, double (*s_part)[20]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ob == N + E) {
-    // cost = 1/2 sum r^2: thread t takes constraints t, t + 128, ... four at a time (their loads overlap)
+    // cost = 1/2 sum r^2
     double a = 0;
-    if (!exclude_reg) {
-      for (int c0 = threadIdx.x; c0 < n_reg; c0 += 4 * 128) {
-        int t0[4], t1[4];
-        double f[4], v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c0 + 128 * k;
-          const bool in = c < n_reg;
-          t0[k] = in ? __ldg(sums.tile_begin + c) : 0;
-          t1[k] = in ? __ldg(sums.tile_begin + c + 1) : 0;
-          f[k] = in ? sums.cons[c].factor : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = reg_tile_sum(sums.partials, t0[k], t1[k], 20);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a += v[k] * (f[k] * f[k]);
-      }
-    }
+    if (!exclude_reg)
+      for (int c = threadIdx.x; c < n_reg; c += 128) a += __ldcg(csum + (size_t)c * VGX_REG_NSTRIDE + 20);
     for (int e = threadIdx.x; e < n_rel; e += 128) {
       RelEval R;
       rel_eval(rel[e], x, R);
@@ -301,9 +269,8 @@ __device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
     if (threadIdx.x == 0) {
       const double cst = 0.5 * (((s_part[0][0] + s_part[1][0]) + s_part[2][0]) + s_part[3][0]);
       for (int k = 0; k < push.n; ++k) {
-        double* packed = push.dst[k];
-        packed[0] = cst;
-        packed[1] = 0; packed[2] = 0; packed[3] = 0;
+        vgx_push_store(push, k, 0, cst);
+        vgx_push_store(push, k, 1, 0.0); vgx_push_store(push, k, 2, 0.0); vgx_push_store(push, k, 3, 0.0);
       }
     }
     __syncthreads();
@@ -313,24 +280,21 @@ __device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
   const bool diag = ob < N;
   const int r4 = (lane >> 2) & 3, c4 = lane & 3;
   double acc = 0;
-  for (int base = i0; base < i1; base += VGX_ASM_CHUNK) {
-    const int nc = min(VGX_ASM_CHUNK, i1 - base);
-    // ---- phase A: the 21 sums of every registration item of the chunk, all 128 threads: thread k
-    //      owns (item k / 21, entry k % 21); an item's row of each tile is one coalesced 168-byte read
-    if (!exclude_reg) {
-      for (int k = threadIdx.x; k < nc * VGX_REG_NSUM; k += 128) {
-        const int j = k / VGX_REG_NSUM, e = k - j * VGX_REG_NSUM;
-        const int4 it = __ldg(items + base + j);
-        if (it.x >= 0) {
-          const double f = sums.cons[it.x].factor;
-          s_sums[j][e] = reg_tile_sum(sums.partials, it.z, it.w, e) * (f * f);
-        }
-      }
+  // warp w expands items w, w + 4, ... in list order; two items per trip so their loads overlap
+  for (int i = i0 + warp; i < i1; i += 8) {
+    const bool two = i + 4 < i1;
+    const int4 itA = __ldg(items + i);
+    const int4 itB = two ? __ldg(items + i + 4) : make_int4(-1, 0, 0, 0);
+    double svA = 0.0, svB = 0.0;
+    if (!exclude_reg && lane < VGX_REG_NSUM) {
+      if (itA.x >= 0) svA = __ldcg(csum + (size_t)itA.x * VGX_REG_NSTRIDE + lane);
+      if (two && itB.x >= 0) svB = __ldcg(csum + (size_t)itB.x * VGX_REG_NSTRIDE + lane);
     }
-    __syncthreads();
-    // ---- phase B: warp w expands items w, w + 4, ... of the chunk in list order
-    for (int j = warp; j < nc; j += 4) {
-      const int4 it = __ldg(items + base + j);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const int4 it = h ? itB : itA;
+      const double sv = h ? svB : svA;
       // (row, col) of the residual block's 8x8 this lane needs; lanes 16..19: gradient row
       int row, col;
       if (lane < 16) {
@@ -359,7 +323,8 @@ __device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
         } else {
           idx = 15 + ma;
         }
-        acc += sgn * s_sums[j][idx];
+        const double v = __shfl_sync(0xffffffffu, sv, idx);
+        acc += sgn * v;
       } else {
         RelEval R;
         rel_eval(rel[-it.x - 1], x, R);
@@ -374,7 +339,6 @@ __device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
         acc += v;
       }
     }
-    __syncthreads();   // the chunk's sums are consumed before the next chunk overwrites them
   }
   if (lane < 20) s_part[warp][lane] = acc;
   __syncthreads();
@@ -383,63 +347,47 @@ __device__ __forceinline__ void assemble_block(int ob, const RegSums& sums,
     // single rank: one local destination; peer exchange: the value goes to this rank's slot in
     // every rank's region (posted stores over NVLink)
     for (int k = 0; k < push.n; ++k) {
-      double* packed = push.dst[k];
-      if (lane < 16) packed[PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane] = tot;
-      else if (diag) packed[PACK_HDR + 4 * (size_t)ob + (lane - 16)] = tot;
+      if (lane < 16) vgx_push_store(push, k, PACK_HDR + 4 * (size_t)N + 16 * (size_t)ob + lane, tot);
+      else if (diag) vgx_push_store(push, k, PACK_HDR + 4 * (size_t)ob + (lane - 16), tot);
     }
   }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(128)
-assemble_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
+assemble_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
                 const double* __restrict__ x, const int* __restrict__ csr_begin,
                 const int4* __restrict__ items, VgxP2PPush push, int N, int E, int n_reg,
-                int n_rel, int exclude_reg, VgxP2PSignal sig, const int* __restrict__ skip) {
+                int n_rel, int exclude_reg, const int* __restrict__ skip) {
   __shared__ double s_part[4][20];
-  __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
   if (skip && *skip) return;   // evaluation enqueued ahead of a solve that has already ended
-  // programmatic dependent of the reduce kernel: scheduled while that grid drains, blocked here until
-  // it has completed and its tile sums are visible
+  // programmatic dependent of the constraint-sum kernel (itself one of the reduce kernel): scheduled
+  // while those grids drain, blocked here until the sums are visible
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // next evaluation's pose set-up
-  assemble_block(blockIdx.x, sums, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part, s_sums);
-  assemble_signal(sig);
+  assemble_block(blockIdx.x, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
 }
 
 // Fused compute + collective (multi-rank, peer exchange): ONE launch assembles this rank's
-// partial, PUSHES every value into its slot of every rank's NVLink-mapped region while it is
-// produced, publishes the epoch flag to all peers, waits for the peers' flags and adds the n
-// local slots in rank order.  The grid is persistent and sized to be fully co-resident, so waiting
-// CTAs can never starve a CTA that still has to produce: phase 1 never waits, phase 2 only waits
-// on flags that phase 1 of every rank sets.
+// partial and PUSHES every element, tagged with the evaluation's epoch, into its slot of every rank's
+// NVLink-mapped region while it is produced; the same CTAs then spin on the tagged elements of the n
+// local slots and add them in rank order.  No fence, ticket or flag sits between producing a value
+// and a peer consuming it.  The grid is persistent and sized to be fully co-resident, so spinning
+// CTAs can never starve a CTA (here or on a peer) that still has to produce.
 __global__ void __launch_bounds__(128)
-assemble_exchange_kernel(RegSums sums, const VgxRelEdge* __restrict__ rel,
+assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __restrict__ rel,
                          const double* __restrict__ x, const int* __restrict__ csr_begin,
                          const int4* __restrict__ items, VgxP2PPush push, int N, int E,
-                         int n_reg, int n_rel, int exclude_reg, VgxP2PSignal sig, VgxP2PGather gat,
+                         int n_reg, int n_rel, int exclude_reg, VgxP2PGather gat,
                          double* __restrict__ out, int count, const int* __restrict__ skip) {
   if (skip && *skip) return;   // identical on every rank (the ranks' solver states are bit-identical)
   __shared__ double s_part[4][20];
-  __shared__ double s_sums[VGX_ASM_CHUNK][VGX_REG_NSUM];
-  __shared__ int s_ok;
   asm volatile("griddepcontrol.wait;" ::: "memory");   // see assemble_kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int ob = blockIdx.x; ob <= N + E; ob += gridDim.x)
-    assemble_block(ob, sums, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part, s_sums);
-  assemble_signal(sig);
-  // ---- phase 2: wait for every rank's flag in OUR region, then add our slice of the local slots
-  if (threadIdx.x == 0) {
-    s_ok = vgx_p2p_wait(gat) ? 1 : 0;
-    __threadfence_system();
-  }
-  __syncthreads();
-  const bool ok = s_ok != 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < gat.nranks; ++r) s += *((const volatile double*)(gat.slot[r] + i));
-    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // poison on timeout
-  }
+    assemble_block(ob, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
+  vgx_ll_gather(gat, out, (size_t)count, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+                (size_t)gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -646,7 +594,8 @@ __device__ __forceinline__ void dmma_sub_8x8x4(double& c0, double& c1, double a,
 #define CS_NB 8
 __global__ void __launch_bounds__(512)
 chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__ xsol,
-                       LmState* __restrict__ st) {
+                       LmState* __restrict__ st, const int* __restrict__ red,
+                       const int* __restrict__ block_nodes, int N, int E) {
   extern __shared__ double S[];  // packed columns: column j holds rows j..n
   __shared__ int s_fail;
   if (st->done) return;
@@ -655,10 +604,23 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
   const int g = lane >> 2, t = lane & 3;
   double* rinv = S + tri_off(M, M);  // n reciprocals of the diagonal of L
   if (tid == 0) s_fail = 0;
-  for (int j = warp; j < M; j += nw) {
-    const int o = tri_off(j, M);
-    for (int i = j + lane; i < M; i += 32) S[o + i - j] = A[(size_t)j * M + i];
+  // Only the 4x4 blocks lm_build wrote are read (N diagonal, E off-diagonal, the gradient row):
+  // ~5 k loads instead of the dense (n+1)^2, and the matrix in global memory needs no clearing.
+  for (int i = tid; i < tri_off(M, M); i += T) S[i] = 0.0;
+  __syncthreads();
+  for (int t0 = tid; t0 < N * 16; t0 += T) {
+    const int node = t0 >> 4, r = (t0 >> 2) & 3, c = t0 & 3;
+    const int off = red[node];
+    if (off < 0 || r < c) continue;
+    S[tri_off(off + c, M) + (r - c)] = A[(size_t)(off + c) * M + off + r];
   }
+  for (int t0 = tid; t0 < E * 16; t0 += T) {
+    const int b = t0 >> 4, r = (t0 >> 2) & 3, c = t0 & 3;
+    const int oi = red[block_nodes[2 * b]], oj = red[block_nodes[2 * b + 1]];
+    if (oi < 0 || oj < 0) continue;
+    S[tri_off(oi + r, M) + (oj + c) - (oi + r)] = A[(size_t)(oi + r) * M + (oj + c)];
+  }
+  for (int k = tid; k < n; k += T) S[tri_off(k, M) + n - k] = A[(size_t)k * M + n];
   __syncthreads();
   for (int J0 = 0; J0 < n; J0 += CS_NB) {
     const int nb = min(CS_NB, n - J0);
@@ -1411,7 +1373,7 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     if (g->evals_since_order >= 0) ++g->evals_since_order;
     {
-      VgxLaunchScope s(c, 5);
+      VgxLaunchScope s(c, 6);
       vgx_launch_reg_pose_setup(st, g->d_cons, d_x, g->d_poses, g->n_local, skip);
     }
     {
@@ -1424,16 +1386,13 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   // multi-rank peer path: the assembly pushes this rank's partial into every rank's region
   const bool p2p = c->nranks > 1 && c->p2p_ready;
   VgxP2PPush push;
-  VgxP2PSignal sig;
   VgxP2PGather gat;
   memset(&push, 0, sizeof(push));
-  memset(&sig, 0, sizeof(sig));
   memset(&gat, 0, sizeof(gat));
   push.n = 1;
   push.dst[0] = d_packed;
-  RegSums sums;
-  sums.partials = g->d_partials; sums.tile_begin = g->d_tile_begin; sums.cons = g->d_cons;
-  // both assembly kernels are launched as programmatic dependents of what precedes them on the stream
+  // the assembly kernels and the constraint-sum kernel are launched as programmatic dependents of
+  // what precedes them on the stream
   cudaLaunchAttribute pdl[1];
   pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   pdl[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1445,8 +1404,15 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
   cfg.attrs = pdl;
   cfg.numAttrs = (no_pdl && no_pdl[0] == '1') ? 0 : 1;
   const int excl = do_reg ? 0 : 1;
+  if (do_reg) {
+    RegSums sums;
+    sums.partials = g->d_partials; sums.tile_begin = g->d_tile_begin; sums.cons = g->d_cons;
+    VgxLaunchScope s(c, 7);
+    cfg.gridDim = dim3((unsigned)((g->n_local + 3) / 4));
+    cudaLaunchKernelEx(&cfg, reg_csum_kernel, sums, g->n_local, g->d_csum, skip);
+  }
   if (p2p) {
-    int rc = vgx_p2p_begin(c, g->packed_len, &push, &sig, &gat);
+    int rc = vgx_p2p_begin(c, g->packed_len, &push, &gat);
     if (rc != VGX_OK) return rc;
   }
   if (p2p && c->p2p_fused && g->packed_len < (size_t)INT_MAX) {
@@ -1461,20 +1427,20 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
     }
     const int grid = std::min(g->N + g->E + 1, std::min(resident, 592));
     {
-      VgxLaunchScope s(c, 5);
+      VgxLaunchScope s(c, 8);
       cfg.gridDim = dim3((unsigned)grid);
-      cudaLaunchKernelEx(&cfg, assemble_exchange_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x,
+      cudaLaunchKernelEx(&cfg, assemble_exchange_kernel, (const double*)g->d_csum, (const VgxRelEdge*)g->d_rel, d_x,
                          (const int*)g->d_csr_begin, (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local,
-                         g->n_rel_local, excl, sig, gat, d_packed, (int)g->packed_len, skip);
+                         g->n_rel_local, excl, gat, d_packed, (int)g->packed_len, skip);
     }
     VGX_CUDA(c, cudaGetLastError());
     return VGX_OK;
   }
   {
-    VgxLaunchScope s(c, 5);
+    VgxLaunchScope s(c, 8);
     cfg.gridDim = dim3((unsigned)(g->N + g->E + 1));
-    cudaLaunchKernelEx(&cfg, assemble_kernel, sums, (const VgxRelEdge*)g->d_rel, d_x, (const int*)g->d_csr_begin,
-                       (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, sig, skip);
+    cudaLaunchKernelEx(&cfg, assemble_kernel, (const double*)g->d_csum, (const VgxRelEdge*)g->d_rel, d_x, (const int*)g->d_csr_begin,
+                       (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, skip);
   }
   VGX_CUDA(c, cudaGetLastError());
   if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len);
@@ -1700,12 +1666,6 @@ extern "C" int vgx_graph_registration_costs(vgx_ctx* c, double* per_constraint) 
   if (rc != VGX_OK) return rc;
   const int P = (int)g->reg_ref.size();
   std::vector<double> cs((size_t)g->n_local * VGX_REG_NSTRIDE + 1);
-  if (g->n_local > 0) {
-    RegSums sums;
-    sums.partials = g->d_partials; sums.tile_begin = g->d_tile_begin; sums.cons = g->d_cons;
-    reg_csum_kernel<<<(g->n_local + 3) / 4, 128, 0, c->stream>>>(sums, g->n_local, g->d_csum);
-    c->launches++;
-  }
   if (g->n_local > 0)
     VGX_CUDA(c, cudaMemcpyAsync(cs.data(), g->d_csum, sizeof(double) * VGX_REG_NSTRIDE * g->n_local,
                                 cudaMemcpyDeviceToHost, c->stream));
@@ -1995,7 +1955,8 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
   auto enqueue_iteration = [&](int k) -> int {
     {
       VgxLaunchScope s(c, 4, 4);
-      VGX_CUDA(c, cudaMemsetAsync(g->d_A, 0, sizeof(double) * (size_t)(n + 1) * (n + 1), st));
+      if (!use_smem_chol)   // the shared-memory solver reads the written blocks only
+        VGX_CUDA(c, cudaMemsetAsync(g->d_A, 0, sizeof(double) * (size_t)(n + 1) * (n + 1), st));
       const int nthreads = std::max(16 * (N + g->E), 4 * N);
       lm_build_kernel<<<std::min(296, (nthreads + 255) / 256), 256, 0, st>>>(
           g->d_packed[0], g->d_red_offset, g->d_block_nodes, N, g->E, n, g->d_A, g->d_scale, g->d_diag,
@@ -2003,7 +1964,8 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
       lm_persist_kernel<<<1, 256, 0, st>>>(g->d_packed[0], g->d_red_offset, N, g->d_scale, g->d_diag,
                                            g->d_state, lo);
       if (use_smem_chol) {
-        chol_solve_smem_kernel<<<1, 512, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state);
+        chol_solve_smem_kernel<<<1, 512, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state, g->d_red_offset,
+                                                                g->d_block_nodes, N, g->E);
       } else if (coop_grid > 0) {
         int n_arg = n;
         void* args[] = {(void*)&g->d_A, (void*)&n_arg, (void*)&g->d_state};

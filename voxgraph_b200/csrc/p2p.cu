@@ -1,9 +1,10 @@
 // One-shot all-gather-reduce of the packed normal equations over NVLink peer memory (CUDA IPC):
-// PUSH variant.  See vgx_comm_p2p_export / vgx_comm_p2p_import in include/voxgraph_b200.h and the
-// protocol description in vgx_internal.h.
+// PUSH variant with tagged 16-byte words.  See vgx_comm_p2p_export / vgx_comm_p2p_import in
+// include/voxgraph_b200.h and the protocol description in vgx_internal.h.
 //
 // Two parities suffice: a rank can only push epoch e+2 after its own gather of e+1 has finished
-// (stream order), which needs every rank's flag e+1, which a rank sets only after its gather of e.
+// (stream order), which needs every rank's elements of e+1, which a rank pushes only after its
+// gather of e.
 #include <stdlib.h>
 #include <string.h>
 
@@ -11,22 +12,12 @@
 
 #define P2P_FLAG_BYTES 256
 #define P2P_MAX_RANKS 8
+#define P2P_ELEM_BYTES 16   // {value.lo32, tag, value.hi32, tag}
 
-// separate-launch gather (VGX_P2P_FUSED=0): wait for the flags, add the local slots in rank order
+// separate-launch gather (VGX_P2P_FUSED=0): spin on the tagged elements, add them in rank order
 __global__ void __launch_bounds__(256)
 p2p_gather_kernel(VgxP2PGather G, double* __restrict__ out, size_t count) {
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    s_ok = vgx_p2p_wait(G) ? 1 : 0;
-    __threadfence_system();
-  }
-  __syncthreads();
-  const bool ok = s_ok != 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < G.nranks; ++r) s += *((const volatile double*)(G.slot[r] + i));
-    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // poison on timeout: LM sees an invalid step
-  }
+  vgx_ll_gather(G, out, count, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
 void vgx_p2p_free(vgx_ctx* c) {
@@ -48,7 +39,7 @@ extern "C" int vgx_comm_p2p_export(vgx_ctx* c, uint64_t capacity_doubles, uint8_
   vgx_p2p_free(c);
   const size_t cap = ((size_t)capacity_doubles + 31) & ~(size_t)31;
   // the rank count is not known yet: room for the 8 source ranks of one node, two parities
-  const size_t bytes = P2P_FLAG_BYTES + 2 * (size_t)P2P_MAX_RANKS * cap * sizeof(double);
+  const size_t bytes = P2P_FLAG_BYTES + 2 * (size_t)P2P_MAX_RANKS * cap * P2P_ELEM_BYTES;
   VGX_CUDA(c, cudaMalloc(&c->p2p_base, bytes));
   VGX_CUDA(c, cudaMemset(c->p2p_base, 0, bytes));
   cudaIpcMemHandle_t h;
@@ -107,31 +98,26 @@ int vgx_p2p_check(vgx_ctx* c) {
   return VGX_OK;
 }
 
-static inline double* p2p_slot(void* region, size_t cap, unsigned long long epoch, int src_rank) {
-  return (double*)((char*)region + P2P_FLAG_BYTES) + ((epoch & 1) * P2P_MAX_RANKS + (size_t)src_rank) * cap;
+static inline char* p2p_slot(void* region, size_t cap, unsigned long long epoch, int src_rank) {
+  return (char*)region + P2P_FLAG_BYTES + ((epoch & 1) * P2P_MAX_RANKS + (size_t)src_rank) * cap * P2P_ELEM_BYTES;
 }
 
-int vgx_p2p_begin(vgx_ctx* c, size_t count, VgxP2PPush* push, VgxP2PSignal* sig, VgxP2PGather* gat) {
+int vgx_p2p_begin(vgx_ctx* c, size_t count, VgxP2PPush* push, VgxP2PGather* gat) {
   if (!c->p2p_ready) VGX_FAIL(c, VGX_ERR_INVALID, "peer exchange not initialised");
   if (count > c->p2p_cap) VGX_FAIL(c, VGX_ERR_CAPACITY, "packed normal equations exceed the exported peer buffer");
-  const unsigned long long e = ++c->p2p_epoch;
+  unsigned long long e = ++c->p2p_epoch;
+  if ((unsigned)e == 0u) e = (c->p2p_epoch += 2);   // tag 0 means "never written"; keep the parity alternating
   memset(push, 0, sizeof(*push));
-  memset(sig, 0, sizeof(*sig));
   memset(gat, 0, sizeof(*gat));
   push->n = c->nranks;
-  sig->epoch = e;
-  sig->nranks = c->nranks;
-  sig->rank = c->rank;
-  sig->counter = (int*)((char*)c->p2p_base + 192);  // local word of the flag page
-  gat->flags = (const unsigned long long*)c->p2p_base;
-  gat->timeout_flag = (int*)((char*)c->p2p_base + 128);  // local word of the flag page, peers never touch it
+  push->tag = (unsigned)e;
+  gat->timeout_flag = (int*)((char*)c->p2p_base + 128);  // local word of the page, peers never touch it
   gat->timeout_cycles = c->p2p_timeout_cycles;
-  gat->epoch = e;
+  gat->tag = (unsigned)e;
   gat->nranks = c->nranks;
   for (int r = 0; r < c->nranks; ++r) {
-    push->dst[r] = p2p_slot(c->p2p_peer[r], c->p2p_cap, e, c->rank);   // my slot in rank r's region
-    sig->flags[r] = (unsigned long long*)c->p2p_peer[r];
-    gat->slot[r] = p2p_slot(c->p2p_base, c->p2p_cap, e, r);            // rank r's slot in my region
+    push->dst[r] = (double*)p2p_slot(c->p2p_peer[r], c->p2p_cap, e, c->rank);   // my slot in rank r's region
+    gat->slot[r] = p2p_slot(c->p2p_base, c->p2p_cap, e, r);                    // rank r's slot in my region
   }
   return VGX_OK;
 }

@@ -133,7 +133,7 @@ extern "C" int vgx_profile_reset(vgx_ctx* c) {
   return VGX_OK;
 }
 extern "C" int vgx_profile_get(vgx_ctx* c, int which, double* total_ms, int64_t* launches) {
-  if (!c || which < 0 || which >= 6) return VGX_ERR_INVALID;
+  if (!c || which < 0 || which >= 10) return VGX_ERR_INVALID;
   if (total_ms) *total_ms = c->prof[which].total_ms;
   if (launches) *launches = c->prof[which].launches;
   return VGX_OK;

@@ -147,7 +147,7 @@ struct vgx_ctx {
   VgxGraph* graph = nullptr;
   // profiling
   bool profile = false;
-  VgxProfileSlot prof[6];
+  VgxProfileSlot prof[10];
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch
@@ -220,42 +220,66 @@ void vgx_graph_invalidate_registration(vgx_ctx* ctx);
 // NCCL (dlopen'ed, nccl_dyn.cpp)
 int vgx_nccl_allreduce_sum_f64(vgx_ctx* ctx, double* d_buf, size_t count);
 
-// NVLink peer exchange (p2p.cu): PUSH all-gather + local reduce.
-// Every rank owns a CUDA-IPC exported region [flags 256 B | slot[parity 2][source rank 8][cap]].
-// An evaluation (epoch e, parity e & 1): the assembly kernel stores each value of the rank's partial
-// straight into slot[parity][rank] of EVERY rank's region (posted NVLink writes), fences, and its
-// last CTA stores e into flag[rank] of every region; the receiver waits for its own n flags and
-// adds its n local slots in rank order (no load ever crosses NVLink; bit-identical on all ranks).
+// NVLink peer exchange (p2p.cu): PUSH all-gather + local reduce with TAGGED WORDS (the low-latency
+// protocol of NCCL's LL transport, restated for doubles).
+// Every rank owns a CUDA-IPC exported region [page 256 B | slot[parity 2][source rank 8][cap x 16 B]].
+// An element travels as one 16-byte store {value.lo32, tag, value.hi32, tag}, tag = the evaluation's
+// epoch (never 0; the region starts zeroed).  An evaluation (epoch e, parity e & 1): the assembly kernel
+// stores every element of the rank's partial straight into slot[parity][rank] of EVERY rank's region
+// while it is produced (posted NVLink writes) - no fence, no ticket, no flag.  The receiver spins on
+// each element of its n local slots until both tags read e, and adds the n values in rank order (no
+// load ever crosses NVLink; bit-identical on all ranks).  8-byte halves of a store are each atomic,
+// which is all the tag check relies on.
 struct VgxP2PPush {
   double* dst[8];   // where this rank's partial goes: one destination per rank (n == 1: local buffer)
   int n;
-};
-struct VgxP2PSignal {
-  unsigned long long* flags[8];  // flag array of every rank (peer-mapped)
-  unsigned long long epoch;
-  int* counter;                  // local ticket counter (finished CTAs)
-  int nranks, rank;              // nranks == 0: disabled
+  unsigned tag;     // != 0: the destinations are tagged 16-byte slots; 0: plain doubles
 };
 struct VgxP2PGather {
-  const double* slot[8];         // this epoch's local slots, one per source rank
-  const unsigned long long* flags;   // own flag array
+  const void* slot[8];           // this epoch's local slots, one per source rank (16 bytes per element)
   int* timeout_flag;
   long long timeout_cycles;
-  unsigned long long epoch;
+  unsigned tag;
   int nranks;
 };
-int vgx_p2p_begin(vgx_ctx* ctx, size_t count, VgxP2PPush* push, VgxP2PSignal* sig, VgxP2PGather* gat);
+int vgx_p2p_begin(vgx_ctx* ctx, size_t count, VgxP2PPush* push, VgxP2PGather* gat);
 int vgx_p2p_gather(vgx_ctx* ctx, const VgxP2PGather& gat, double* d_out, size_t count);  // separate-launch variant
 void vgx_p2p_free(vgx_ctx* ctx);
 int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out (the flag is cleared)
 #ifdef __CUDACC__
-// waits for the n flags (thread 0 of the CTA), returns false on timeout
-__device__ __forceinline__ bool vgx_p2p_wait(const VgxP2PGather& G) {
-  const volatile unsigned long long* mine = G.flags;
+__device__ __forceinline__ void vgx_push_store(const VgxP2PPush& P, int k, size_t idx, double v) {
+  if (P.tag == 0) { P.dst[k][idx] = v; return; }
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};"
+               ::"l"(reinterpret_cast<uint4*>(P.dst[k]) + idx), "r"((unsigned)b), "r"(P.tag), "r"((unsigned)(b >> 32))
+               : "memory");
+}
+// element idx of source rank r: spins until both tags match; false on timeout
+__device__ __forceinline__ bool vgx_ll_load(const VgxP2PGather& G, int r, size_t idx, long long t0, double& v) {
+  const uint4* p = reinterpret_cast<const uint4*>(G.slot[r]) + idx;
+  for (;;) {
+    unsigned x, y, z, w;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(p) : "memory");
+    if (y == G.tag && w == G.tag) {
+      v = __longlong_as_double((long long)(((unsigned long long)z << 32) | x));
+      return true;
+    }
+    if (clock64() - t0 > G.timeout_cycles) return false;
+  }
+}
+// out[i] = sum over ranks of element i (rank order); NaN-poisoned when a rank never delivered
+__device__ __forceinline__ void vgx_ll_gather(const VgxP2PGather& G, double* __restrict__ out, size_t count,
+                                              size_t first, size_t stride) {
   const long long t0 = clock64();
-  for (int r = 0; r < G.nranks; ++r)
-    while (mine[r] < G.epoch)
-      if (clock64() - t0 > G.timeout_cycles) { *G.timeout_flag = 1; return false; }
-  return true;
+  for (size_t i = first; i < count; i += stride) {
+    double s = 0.0;
+    bool ok = true;
+    for (int r = 0; r < G.nranks; ++r) {
+      double v = 0.0;
+      if (ok && !vgx_ll_load(G, r, i, t0, v)) { ok = false; *G.timeout_flag = 1; }
+      s += v;
+    }
+    out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // the LM sees an invalid step
+  }
 }
 #endif
