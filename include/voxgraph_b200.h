@@ -328,11 +328,13 @@ int vgx_comm_init(vgx_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
 int vgx_comm_destroy(vgx_ctx* ctx);
 /* NVLink peer-memory exchange (single node, <= 8 ranks): replaces the NCCL all-reduce of the
  * packed normal equations by a one-shot all-gather-reduce over CUDA-IPC mapped peer buffers:
- * the assembly kernel writes the rank's partial into its exported buffer, a flag store signals
- * every peer, and each rank sums all partials in rank order straight out of peer memory
- * (bit-identical on all ranks). export: allocate + get the 64-byte IPC handle; import: map
- * the peers (handles = nranks x 64 bytes, own entry ignored). Works with or without
- * vgx_comm_init; when both are set the peer path is used. */
+ * the assembly kernel PUSHES every element of the rank's partial, tagged with the evaluation's
+ * epoch (one 16-byte store {lo32, tag, hi32, tag}), into its slot of every peer's exported
+ * region while it is produced; each rank then spins on the tagged elements of its own region and
+ * sums the partials in rank order (no load crosses NVLink, no fence or flag; bit-identical on all
+ * ranks).  export: allocate 2 parities x 8 ranks x capacity_doubles x 16 bytes + get the 64-byte
+ * IPC handle; import: map the peers (handles = nranks x 64 bytes, own entry ignored). Works with
+ * or without vgx_comm_init; when both are set the peer path is used. */
 /* Self-check of the sharded evaluation: while suspended (on = 1) the context behaves as a
  * single-rank context - it evaluates EVERY constraint locally and skips the exchange - so a rank
  * can compare the all-reduced result with the full problem computed on one GPU (all submaps are

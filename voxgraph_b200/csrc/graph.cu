@@ -667,57 +667,57 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
       }
     }
     __syncthreads();
-    // (2) factor the diagonal block: warp 0, lane r holds row r of the 8x8 block in registers,
-    //     pivots and multipliers travel by shuffle (no shared-memory round trips on the serial path)
-    if (warp == 0) {
-      double row[CS_NB];
+    // (2)+(3) EVERY thread factors the 8x8 diagonal block redundantly in registers - no serial warp,
+    // no shuffles on the pivot chain (chain per column: rsqrt, mul, fma) - and then forward-substitutes
+    // its own row (thread t owns row J0 + t; the block's own rows come out of the same recurrence,
+    // restricted to the lower triangle, bit-identical to the register factor).
+    {
+      const int r = J0 + tid;
+      const int i = tid;            // row inside / below the block
+      const bool act = r < M;
+      double Lb[CS_NB][CS_NB], x[CS_NB], ri[CS_NB];
 #pragma unroll
-      for (int c = 0; c < CS_NB; ++c)
-        row[c] = (lane < nb && c <= lane && c < nb) ? S[tri_off(J0 + c, M) + lane - c] : 0.0;
+      for (int c = 0; c < CS_NB; ++c) {
+#pragma unroll
+        for (int q = 0; q < CS_NB; ++q)
+          if (q >= c) Lb[q][c] = (q < nb && c < nb) ? S[tri_off(J0 + c, M) + q - c] : (q == c ? 1.0 : 0.0);
+        x[c] = (act && c < nb && (i >= nb || c <= i)) ? S[tri_off(J0 + c, M) + r - (J0 + c)] : 0.0;
+      }
+      __syncthreads();   // every thread has read the unfactored block before any row is written back
+      bool bad = false;
 #pragma unroll
       for (int k = 0; k < CS_NB; ++k) {
-        if (k < nb) {
-          double d = __shfl_sync(0xffffffffu, row[k], k);
-          if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = 1; d = 1.0; }
-          const double rs = fast_rsqrt(d);
-          if (lane == k) { row[k] = d * rs; rinv[J0 + k] = rs; }
-          else if (lane > k) row[k] *= rs;
-          const double lik = row[k];
+        double d = Lb[k][k];
+        if (k < nb && (!(d > 0.0) || !isfinite(d))) { bad = true; d = 1.0; }
+        const double rs = fast_rsqrt(d);
+        ri[k] = rs;
+        Lb[k][k] = d * rs;
 #pragma unroll
-          for (int c = k + 1; c < CS_NB; ++c) {
-            const double lck = __shfl_sync(0xffffffffu, lik, c);  // L[c][k]
-            if (lane >= c) row[c] = fma(-lik, lck, row[c]);
-          }
-        }
-      }
+        for (int q = k + 1; q < CS_NB; ++q) Lb[q][k] *= rs;
 #pragma unroll
-      for (int c = 0; c < CS_NB; ++c)
-        if (lane < nb && c <= lane && c < nb) S[tri_off(J0 + c, M) + lane - c] = row[c];
-    }
-    __syncthreads();
-    // (3) panel solve: rows below the block (incl. the rhs row n).  The 8x8 block and the row's eight
-    //     entries are loaded first, so the substitution chain runs on registers only.
-    for (int r = J0 + nb + tid; r < M; r += T) {
-      double x[CS_NB], Lb[CS_NB][CS_NB];
+        for (int c = k + 1; c < CS_NB; ++c)
 #pragma unroll
-      for (int c = 0; c < CS_NB; ++c) {
-        x[c] = (c < nb) ? S[tri_off(J0 + c, M) + r - (J0 + c)] : 0.0;
-#pragma unroll
-        for (int k = 0; k < CS_NB; ++k) Lb[c][k] = (k < c && c < nb) ? S[tri_off(J0 + k, M) + c - k] : 0.0;
+          for (int q = c; q < CS_NB; ++q) Lb[q][c] = fma(-Lb[q][k], Lb[c][k], Lb[q][c]);
       }
 #pragma unroll
       for (int c = 0; c < CS_NB; ++c) {
-        if (c < nb) {
-          double v = x[c];
+        double v = x[c];
 #pragma unroll
-          for (int k = 0; k < CS_NB; ++k)
-            if (k < c) v -= x[k] * Lb[c][k];
-          x[c] = v * rinv[J0 + c];
-        }
+        for (int k = 0; k < CS_NB; ++k)
+          if (k < c) v = fma(-x[k], Lb[c][k], v);
+        x[c] = v * ri[c];
       }
+      if (act) {
 #pragma unroll
-      for (int c = 0; c < CS_NB; ++c)
-        if (c < nb) S[tri_off(J0 + c, M) + r - (J0 + c)] = x[c];
+        for (int c = 0; c < CS_NB; ++c)
+          if (c < nb && (i >= nb || c <= i)) S[tri_off(J0 + c, M) + r - (J0 + c)] = x[c];
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < CS_NB; ++k)
+          if (k < nb) rinv[J0 + k] = ri[k];
+        if (bad) s_fail = 1;
+      }
     }
     __syncthreads();
   }
