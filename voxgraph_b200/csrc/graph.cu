@@ -73,6 +73,7 @@ struct VgxGraph {
   double* d_csum = nullptr;
   VgxRelEdge* d_rel = nullptr;
   int* d_counters = nullptr;    // (unused)
+  unsigned char* d_block_mask = nullptr;   // per output block: bit r = rank r contributes (peer exchange)
   int* d_tile_order = nullptr;  // one-CTA-per-tile mode: CTA b runs tile d_tile_order[b] (longest first)
   int* d_tile_cost = nullptr;   // SM cycles each tile took in the latest evaluation
   bool hw_tiles = false;
@@ -104,8 +105,8 @@ struct VgxGraph {
 static void free_tables(VgxGraph* g) {
   cudaFree(g->d_cons); cudaFree(g->d_poses); cudaFree(g->d_tiles); cudaFree(g->d_tile_begin); cudaFree(g->d_cta_tile_begin);
   cudaFree(g->d_partials); cudaFree(g->d_csum); cudaFree(g->d_rel); cudaFree(g->d_counters);
-  cudaFree(g->d_tile_order); cudaFree(g->d_tile_cost);
-  g->d_tile_order = nullptr; g->d_tile_cost = nullptr;
+  cudaFree(g->d_tile_order); cudaFree(g->d_tile_cost); cudaFree(g->d_block_mask);
+  g->d_tile_order = nullptr; g->d_tile_cost = nullptr; g->d_block_mask = nullptr;
   cudaFree(g->d_csr_begin); cudaFree(g->d_csr_items); cudaFree(g->d_block_nodes);
   cudaFree(g->d_red_offset); cudaFree(g->d_x); cudaFree(g->d_xc);
   cudaFree(g->d_packed[0]); cudaFree(g->d_packed[1]);
@@ -277,6 +278,9 @@ __device__ __forceinline__ void assemble_block(int ob, const double* __restrict_
     return;
   }
   const int i0 = csr_begin[ob], i1 = csr_begin[ob + 1];
+  // peer exchange: a block this rank has nothing for is not pushed (the receivers know from the
+  // block's rank mask that this slot holds no value of this epoch)
+  if (push.tag != 0 && i0 == i1) return;
   const bool diag = ob < N;
   const int r4 = (lane >> 2) & 3, c4 = lane & 3;
   double acc = 0;
@@ -379,7 +383,8 @@ assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __re
                          const double* __restrict__ x, const int* __restrict__ csr_begin,
                          const int4* __restrict__ items, VgxP2PPush push, int N, int E,
                          int n_reg, int n_rel, int exclude_reg, VgxP2PGather gat,
-                         double* __restrict__ out, int count, const int* __restrict__ skip) {
+                         double* __restrict__ out, int count, const int* __restrict__ skip,
+                         const unsigned char* __restrict__ block_mask) {
   if (skip && *skip) return;   // identical on every rank (the ranks' solver states are bit-identical)
   __shared__ double s_part[4][20];
   asm volatile("griddepcontrol.wait;" ::: "memory");   // see assemble_kernel
@@ -387,7 +392,7 @@ assemble_exchange_kernel(const double* __restrict__ csum, const VgxRelEdge* __re
   for (int ob = blockIdx.x; ob <= N + E; ob += gridDim.x)
     assemble_block(ob, csum, rel, x, csr_begin, items, push, N, E, n_reg, n_rel, exclude_reg, s_part);
   vgx_ll_gather(gat, out, (size_t)count, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
-                (size_t)gridDim.x * blockDim.x);
+                (size_t)gridDim.x * blockDim.x, block_mask, N);
 }
 
 // ------------------------------------------------------------------ kernels: LM
@@ -1279,6 +1284,18 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   };
   for (int e = 0; e < g->n_rel_local; ++e) add_items(-(e + 1), g->rel[e].a, g->rel[e].b);
   for (int k = 0; k < g->n_local; ++k) add_items(k, cons[k].ref_node, cons[k].read_node);
+  // which ranks have items for an output block (every rank computes the same table: the partition
+  // of the constraints is global knowledge; relative edges live on rank 0)
+  std::vector<unsigned char> block_mask(N + g->E, 0);
+  for (const auto& e : g->rel) {
+    block_mask[e.a] |= 1; block_mask[e.b] |= 1;
+    block_mask[N + block_id(e.a, e.b)] |= 1;
+  }
+  for (int i = 0; i < P; ++i) {
+    const unsigned char bit = (unsigned char)(1u << owner[i]);
+    block_mask[all[i].ref_node] |= bit; block_mask[all[i].read_node] |= bit;
+    block_mask[N + block_id(all[i].ref_node, all[i].read_node)] |= bit;
+  }
   std::vector<int> csr_begin(N + g->E + 1, 0);
   std::vector<int4> items;   // a registration item carries its constraint's tile range
   for (int ob = 0; ob < N + g->E; ++ob) {
@@ -1313,6 +1330,7 @@ static int build_tables(vgx_ctx* c, VgxGraph* g) {
   if (e == cudaSuccess) e = upload_vec(&g->d_rel, g->rel, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_begin, csr_begin, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_csr_items, items, st);
+  if (e == cudaSuccess) e = upload_vec(&g->d_block_mask, block_mask, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_block_nodes, block_nodes, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_red_offset, red, st);
   if (e == cudaSuccess) e = upload_vec(&g->d_x, g->x, st);
@@ -1425,13 +1443,14 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
         per_sm = 1;
       resident = std::max(1, sms * std::max(per_sm, 1));
     }
-    const int grid = std::min(g->N + g->E + 1, std::min(resident, 592));
+    const int grid = std::min(g->N + g->E + 1, resident);
     {
       VgxLaunchScope s(c, 8);
       cfg.gridDim = dim3((unsigned)grid);
       cudaLaunchKernelEx(&cfg, assemble_exchange_kernel, (const double*)g->d_csum, (const VgxRelEdge*)g->d_rel, d_x,
                          (const int*)g->d_csr_begin, (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local,
-                         g->n_rel_local, excl, gat, d_packed, (int)g->packed_len, skip);
+                         g->n_rel_local, excl, gat, d_packed, (int)g->packed_len, skip,
+                         (const unsigned char*)g->d_block_mask);
     }
     VGX_CUDA(c, cudaGetLastError());
     return VGX_OK;
@@ -1443,7 +1462,7 @@ static int eval_enqueue(vgx_ctx* c, VgxGraph* g, const double* d_x, double* d_pa
                        (const int4*)g->d_csr_items, push, g->N, g->E, g->n_local, g->n_rel_local, excl, skip);
   }
   VGX_CUDA(c, cudaGetLastError());
-  if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len);
+  if (p2p) return vgx_p2p_gather(c, gat, d_packed, g->packed_len, g->d_block_mask, g->N);
   return vgx_nccl_allreduce_sum_f64(c, d_packed, g->packed_len);
 }
 

@@ -16,8 +16,10 @@
 
 // separate-launch gather (VGX_P2P_FUSED=0): spin on the tagged elements, add them in rank order
 __global__ void __launch_bounds__(256)
-p2p_gather_kernel(VgxP2PGather G, double* __restrict__ out, size_t count) {
-  vgx_ll_gather(G, out, count, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+p2p_gather_kernel(VgxP2PGather G, double* __restrict__ out, size_t count,
+                  const unsigned char* __restrict__ block_mask, int N) {
+  vgx_ll_gather(G, out, count, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x,
+                block_mask, N);
 }
 
 void vgx_p2p_free(vgx_ctx* c) {
@@ -122,11 +124,12 @@ int vgx_p2p_begin(vgx_ctx* c, size_t count, VgxP2PPush* push, VgxP2PGather* gat)
   return VGX_OK;
 }
 
-int vgx_p2p_gather(vgx_ctx* c, const VgxP2PGather& gat, double* d_out, size_t count) {
+int vgx_p2p_gather(vgx_ctx* c, const VgxP2PGather& gat, double* d_out, size_t count,
+                   const unsigned char* d_block_mask, int N) {
   {
     VgxLaunchScope s(c, 5);
     const int blocks = (int)((count + 1023) / 1024) > 0 ? (int)((count + 1023) / 1024) : 1;
-    p2p_gather_kernel<<<blocks < 64 ? blocks : 64, 256, 0, c->stream>>>(gat, d_out, count);
+    p2p_gather_kernel<<<blocks < 64 ? blocks : 64, 256, 0, c->stream>>>(gat, d_out, count, d_block_mask, N);
   }
   VGX_CUDA(c, cudaGetLastError());
   return VGX_OK;

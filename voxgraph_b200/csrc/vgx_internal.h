@@ -243,7 +243,8 @@ struct VgxP2PGather {
   int nranks;
 };
 int vgx_p2p_begin(vgx_ctx* ctx, size_t count, VgxP2PPush* push, VgxP2PGather* gat);
-int vgx_p2p_gather(vgx_ctx* ctx, const VgxP2PGather& gat, double* d_out, size_t count);  // separate-launch variant
+int vgx_p2p_gather(vgx_ctx* ctx, const VgxP2PGather& gat, double* d_out, size_t count,
+                   const unsigned char* d_block_mask, int N);  // separate-launch variant
 void vgx_p2p_free(vgx_ctx* ctx);
 int vgx_p2p_check(vgx_ctx* ctx);   // VGX_ERR_NCCL if a gather timed out (the flag is cleared)
 #ifdef __CUDACC__
@@ -267,18 +268,41 @@ __device__ __forceinline__ bool vgx_ll_load(const VgxP2PGather& G, int r, size_t
     if (clock64() - t0 > G.timeout_cycles) return false;
   }
 }
-// out[i] = sum over ranks of element i (rank order); NaN-poisoned when a rank never delivered
+// out[i] = sum over the CONTRIBUTING ranks of element i, in rank order; NaN-poisoned when a rank never
+// delivered.  block_mask[ob] (bit r: rank r has items for output block ob; identical on all ranks,
+// the constraint -> rank partition is global knowledge) tells which slots hold this epoch's value: a
+// rank does not push blocks it has nothing for.  Packed layout: [4 header | 4 N gradient | 16 N
+// diagonal | 16 E off-diagonal]; the header comes from every rank.  All the loads of an element are
+// issued before the first tag is checked.
 __device__ __forceinline__ void vgx_ll_gather(const VgxP2PGather& G, double* __restrict__ out, size_t count,
-                                              size_t first, size_t stride) {
+                                              size_t first, size_t stride,
+                                              const unsigned char* __restrict__ block_mask, int N) {
   const long long t0 = clock64();
+  const unsigned all = (1u << G.nranks) - 1u;
   for (size_t i = first; i < count; i += stride) {
+    unsigned m = all;
+    if (block_mask && i >= 4) {
+      const size_t j = i - 4;
+      m = j < 4 * (size_t)N ? block_mask[j >> 2] : block_mask[(j - 4 * (size_t)N) >> 4];
+    }
+    unsigned x[8], y[8], z[8], w[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < G.nranks && ((m >> r) & 1u)) {
+        const uint4* p = reinterpret_cast<const uint4*>(G.slot[r]) + i;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(x[r]), "=r"(y[r]), "=r"(z[r]), "=r"(w[r]) : "l"(p) : "memory");
+      }
     double s = 0.0;
     bool ok = true;
-    for (int r = 0; r < G.nranks; ++r) {
-      double v = 0.0;
-      if (ok && !vgx_ll_load(G, r, i, t0, v)) { ok = false; *G.timeout_flag = 1; }
-      s += v;
-    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < G.nranks && ((m >> r) & 1u)) {
+        double v = 0.0;
+        if (y[r] == G.tag && w[r] == G.tag) v = __longlong_as_double((long long)(((unsigned long long)z[r] << 32) | x[r]));
+        else if (ok && !vgx_ll_load(G, r, i, t0, v)) { ok = false; *G.timeout_flag = 1; }
+        s += v;
+      }
     out[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);   // the LM sees an invalid step
   }
 }
