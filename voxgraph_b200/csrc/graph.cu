@@ -600,7 +600,7 @@ __device__ __forceinline__ void dmma_sub_8x8x4(double& c0, double& c1, double a,
 __global__ void __launch_bounds__(512)
 chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__ xsol,
                        LmState* __restrict__ st, const int* __restrict__ red,
-                       const int* __restrict__ block_nodes, int N, int E) {
+                       const int* __restrict__ block_nodes, int N, int E, long long* __restrict__ dbg) {
   extern __shared__ double S[];  // packed columns: column j holds rows j..n
   __shared__ int s_fail;
   if (st->done) return;
@@ -609,6 +609,7 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
   const int g = lane >> 2, t = lane & 3;
   double* rinv = S + tri_off(M, M);  // n reciprocals of the diagonal of L
   if (tid == 0) s_fail = 0;
+  long long tk0 = clock64(), tk_upd = 0, tk_fac = 0;   // phase cycles (thread 0, VGX_CHOL_DEBUG=1)
   // Only the 4x4 blocks lm_build wrote are read (N diagonal, E off-diagonal, the gradient row):
   // ~5 k loads instead of the dense (n+1)^2, and the matrix in global memory needs no clearing.
   for (int i = tid; i < tri_off(M, M); i += T) S[i] = 0.0;
@@ -627,8 +628,10 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
   }
   for (int k = tid; k < n; k += T) S[tri_off(k, M) + n - k] = A[(size_t)k * M + n];
   __syncthreads();
+  const long long tk_load = clock64() - tk0;
   for (int J0 = 0; J0 < n; J0 += CS_NB) {
     const int nb = min(CS_NB, n - J0);
+    const long long tp0 = clock64();
     // (1) A[J0.., J0..J0+8) -= L[J0.., 0..J0) * L[J0..J0+8, 0..J0)^T
     if (J0 > 0) {
       const int ntiles = (M - J0 + 7) >> 3;
@@ -672,6 +675,8 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
       }
     }
     __syncthreads();
+    const long long tp1 = clock64();
+    tk_upd += tp1 - tp0;
     // (2)+(3) EVERY thread factors the 8x8 diagonal block redundantly in registers - no serial warp,
     // no shuffles on the pivot chain (chain per column: rsqrt, mul, fma) - and then forward-substitutes
     // its own row (thread t owns row J0 + t; the block's own rows come out of the same recurrence,
@@ -690,6 +695,9 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
       }
       __syncthreads();   // every thread has read the unfactored block before any row is written back
       bool bad = false;
+      // only the warps that own a row run the recurrence (the FP64 pipe of the one SM is the limiter:
+      // 16 redundant copies cost more than the chain itself)
+      if (tid < ((M - J0 + 31) & ~31)) {
 #pragma unroll
       for (int k = 0; k < CS_NB; ++k) {
         double d = Lb[k][k];
@@ -712,6 +720,7 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
           if (k < c) v = fma(-x[k], Lb[c][k], v);
         x[c] = v * ri[c];
       }
+      }
       if (act) {
 #pragma unroll
         for (int c = 0; c < CS_NB; ++c)
@@ -725,7 +734,9 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
       }
     }
     __syncthreads();
+    tk_fac += clock64() - tp1;
   }
+  const long long tk_back0 = clock64();
   // back substitution L^T x = y (y = row n of L, element n of each column): ONE warp, y in
   // registers (lane l owns unknowns l, l + 32, ...).  Step j: the owner scales its y_j, one shuffle
   // broadcasts x_j, every lane folds it into its remaining unknowns with loads that do not depend
@@ -762,6 +773,9 @@ chol_solve_smem_kernel(const double* __restrict__ A, int n, double* __restrict__
     }
   }
   if (tid == 0 && s_fail) st->step_valid = 0;
+  if (dbg && tid == 0) {
+    dbg[0] = tk_load; dbg[1] = tk_upd; dbg[2] = tk_fac; dbg[3] = clock64() - tk_back0; dbg[4] = clock64() - tk0;
+  }
 }
 
 // Multi-CTA variant (cooperative launch, grid-wide barriers): every CTA factors the 32x32
@@ -1970,6 +1984,10 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
   bool timed_out = false;
   static const char* no_spec = getenv("VGX_LM_NO_RUNAHEAD");
   const int ahead = (c->nranks == 1 && !(no_spec && no_spec[0] == '1')) ? 1 : 0;
+  // VGX_CHOL_DEBUG=1: phase cycle counts of the last shared-memory Cholesky, printed after the solve
+  static const char* chol_dbg_env = getenv("VGX_CHOL_DEBUG");
+  long long* d_chol_dbg = nullptr;
+  if (chol_dbg_env && chol_dbg_env[0] == '1' && use_smem_chol) cudaMalloc((void**)&d_chol_dbg, 8 * sizeof(long long));
   const int* skip = &g->d_state->done;
   auto enqueue_iteration = [&](int k) -> int {
     {
@@ -1984,7 +2002,7 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
                                            g->d_state, lo);
       if (use_smem_chol) {
         chol_solve_smem_kernel<<<1, 512, smem_chol_bytes, st>>>(g->d_A, n, g->d_step, g->d_state, g->d_red_offset,
-                                                                g->d_block_nodes, N, g->E);
+                                                                g->d_block_nodes, N, g->E, d_chol_dbg);
       } else if (coop_grid > 0) {
         int n_arg = n;
         void* args[] = {(void*)&g->d_A, (void*)&n_arg, (void*)&g->d_state};
@@ -2049,6 +2067,14 @@ extern "C" int vgx_graph_solve(vgx_ctx* c, const vgx_solver_options* opts, doubl
     VGX_CUDA(c, cudaStreamSynchronize(st));
   }
   if (n == 0) { g->h_state->termination = 2; }
+  if (d_chol_dbg) {
+    long long h[5] = {0, 0, 0, 0, 0};
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_chol_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[vgx] chol n=%d cycles: load %lld update %lld factor+solve %lld back %lld total %lld\n", n, h[0],
+            h[1], h[2], h[3], h[4]);
+    cudaFree(d_chol_dbg);
+  }
   S.iterations = g->h_state->iterations;
   S.num_successful_steps = g->h_state->successful;
   S.num_residual_evals = g->h_state->evals;
