@@ -15,6 +15,10 @@ VARIANTS = {
     "b8": ["-DVGX_REG_THREADS=128", "-DVGX_REG_MIN_BLOCKS=8"],
     "t64_b12": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=12"],
     "t64_b16": ["-DVGX_REG_THREADS=64", "-DVGX_REG_MIN_BLOCKS=16"],
+    # ablations of the final kernel (results are wrong by construction: timing only)
+    "x_nogram": ["-DVGX_X_NOGRAM=1"],
+    "x_nomath": ["-DVGX_X_NOMATH=1"],
+    "x_noload": ["-DVGX_X_NOLOAD=1"],
 }
 
 if __name__ == "__main__":

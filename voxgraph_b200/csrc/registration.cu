@@ -252,7 +252,13 @@ reg_reduce_kernel(const RegConstraintDev* __restrict__ constraints,
       if (work) {
         const float xi = sp[0], yi = sp[32], dist = sp[96], w = sp[128];
         const RegPointResult Q = vgx_reg_math<kJacobian>(s_C, P, xi, yi, dist, w, ok, d, R.ox, R.oy, R.oz);
+#if defined(VGX_X_NOGRAM)
+        // timing ablation only (scripts/build_variants.py x_nogram): no staging, no MMA - results are wrong
+        d0 = fma(Q.r, (double)Q.jr[0] + (double)Q.jr[3] + (double)Q.je3, d0);
+        if (false) {
+#else
         if (kJacobian) {
+#endif
           stage_w[0 * VGX_STAGE_STRIDE] = (double)Q.jr[0];
           stage_w[1 * VGX_STAGE_STRIDE] = (double)Q.jr[1];
           stage_w[2 * VGX_STAGE_STRIDE] = (double)Q.jr[2];
