@@ -283,6 +283,33 @@ class PoseGraph {
   }
   const std::vector<SolverSummary>& getSolverSummaries() const { return solver_summaries_; }
   vgx_solver_options& solverOptions() { return options_; }
+
+  // pose_graph.cpp:117-163: the keys of the map are the submap pairs whose 4 x 4 covariance blocks are
+  // wanted; false where ceres::Covariance::Compute would fail (rank-deficient Jacobian)
+  typedef std::pair<SubmapID, SubmapID> SubmapIdPair;
+  typedef std::array<double, 16> EdgeCovarianceMatrix;   // row-major, rows = parameters of the first submap
+  typedef std::map<SubmapIdPair, EdgeCovarianceMatrix> EdgeCovarianceMap;
+  bool getEdgeCovarianceMap(EdgeCovarianceMap* edge_covariance_map) {
+    if (!edge_covariance_map) throw std::invalid_argument("edge_covariance_map is null");   // CHECK_NOTNULL
+    sync();
+    std::vector<uint32_t> first, second;
+    for (const auto& kv : *edge_covariance_map) {
+      for (SubmapID id : {kv.first.first, kv.first.second})
+        if (!hasSubmapNode(id)) throw std::invalid_argument("Graph contains no node for submap " + std::to_string(id));
+      first.push_back(kv.first.first);
+      second.push_back(kv.first.second);
+    }
+    std::vector<double> cov(16 * first.size());
+    const int rc = vgx_graph_edge_covariances(ctx_.get(), (int)first.size(), first.data(), second.data(), cov.data());
+    if (rc == VGX_ERR_INVALID) return false;
+    ctx_.check(rc);
+    size_t k = 0;
+    for (auto& kv : *edge_covariance_map) {
+      for (int e = 0; e < 16; ++e) kv.second[e] = cov[16 * k + e];
+      ++k;
+    }
+    return true;
+  }
   // per-edge summed squared residual (getVisualizationEdges, pose_graph.cpp:194-207)
   std::vector<double> getRegistrationEdgeResiduals() {
     sync();
