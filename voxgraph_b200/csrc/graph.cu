@@ -1,6 +1,9 @@
 // Pose graph on the device: fused evaluation of all residual blocks into packed
-// normal-equation blocks, NCCL all-reduce across ranks, and a device-resident
-// Levenberg-Marquardt with Ceres' default trust-region schedule.
+// normal-equation blocks (pose set-up -> reduce -> per-constraint sums -> assembly, chained by
+// programmatic dependent launches), exchange across ranks inside the assembly kernel (tagged
+// push over NVLink peer memory; NCCL all-reduce as the fallback), and a device-resident
+// Levenberg-Marquardt with Ceres' default trust-region schedule that runs one iteration ahead of
+// the host.
 //
 // Reference: voxgraph/src/backend/pose_graph.cpp:48-106 (constraints, optimize()),
 // include/voxgraph/backend/constraint/cost_functions/relative_pose_cost_function_inl.h:8-70,
